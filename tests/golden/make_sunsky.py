@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Bake the reference's DEFAULT sun/sky (setup_sunsky(0.5, 0.2), volumeRender.cpp:1388-1390) with the
+reference's own Hosek/Tungsten model (oracle/_ref/libvolpath_ref_sunsky.so, built by
+oracle/build_ref.py from /root/reference/src/sunsky) and store what the reference hands to
+init_envmap / set_sun (volumeRender.cpp:285-330) as a fixture.
+
+Only the sky half (rows j < H/2) varies; the ground half is one constant colour (H.cpp:315-321), so
+the fixture keeps rows 0..H/2-1 (rgb, fp32) + the ground colour.  Run in the build container only
+(it needs /root/reference through the built .so); the fixture is what travels to the GPU box.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+def main():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvolpath_ref_sunsky.so"))
+    W, H = 1024, 512
+    img = np.zeros((H, W, 4), np.float32)
+    sd = np.zeros(3, np.float32)
+    sp = np.zeros(3, np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.ref_bake_sunsky.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, fp, fp, fp]
+    lib.ref_bake_sunsky(0.5, 0.2, W, H, img.ctypes.data_as(fp), sd.ctypes.data_as(fp), sp.ctypes.data_as(fp))
+    sky = img[: H // 2, :, :3].copy()
+    ground = img[H // 2, 0, :3].copy()
+    # alpha is make_float4(c, 1) * 0.02 in the sky half, 1 in the ground half; the kernel ignores it
+    assert np.all(img[H // 2:, :, :3] == ground) and np.all(img[H // 2:, :, 3] == 1.0)
+    assert np.all(img[: H // 2, :, 3] == np.float32(0.02))
+    out = os.path.join(ROOT, "cuda-volpath_b200", "data", "sunsky_default.npz")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    np.savez_compressed(out, sky=sky, ground=ground, sun_dir=sd, sun_power=sp, width=W, height=H)
+    print("sun_dir", sd, "sun_power", sp, "ground", ground, "sky range", sky.min(), sky.max())
+    print(out, os.path.getsize(out))
+
+
+if __name__ == "__main__":
+    main()

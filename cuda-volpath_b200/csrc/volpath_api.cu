@@ -1,0 +1,678 @@
+// volpath_api.cu -- the C ABI of libvolpath_b200.so (include/volpath.h): a handle-based core (vp_*) and
+// the 14 reference-named extern "C" shims the reference's host code binds (src/volumeRender.cpp:117-128,
+// 347-356; defined in src/volumeRender_kernel.cu).  No torch, no C++ types in any signature.
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "volpath_common.cuh"
+#include "volpath_kernels.h"
+
+using namespace vp;
+
+namespace
+{
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define VP_CUDA(x)                                                                                     \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess) return fail((int)e_, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define VP_TRY(x)            \
+    do {                     \
+        int r_ = (x);        \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+template <class T>
+void dev_free(T*& p)
+{
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+}  // namespace
+
+struct vp_context
+{
+    int   device   = 0;
+    int   num_sms  = 0;
+    Scene S;
+    // volume
+    float*    dense       = nullptr;  // dense fp32 value copy (kept on request)
+    uint32_t* table       = nullptr;
+    uint32_t* slot_brick  = nullptr;
+    void*     octets      = nullptr;
+    float2*   bounds_voxel = nullptr;
+    float2*   bounds_cell = nullptr;
+    uint8_t*  top         = nullptr;
+    float*    opacity     = nullptr;
+    float4*   env         = nullptr;
+    uint32_t  n_slots     = 0;
+    size_t    n_bricks    = 0;
+    size_t    octet_bytes = 0;
+    int       bound_D     = 0;
+    bool      have_volume = false;
+    // instrumentation
+    unsigned long long* d_stats = nullptr;
+    bool                stats_on = false;
+    unsigned long long  launches = 0;
+    cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
+    bool                timed = false;
+    float               inv_model[12];
+};
+
+static void scene_defaults(Scene& S)
+{
+    memset(&S, 0, sizeof(S));
+    S.bmin = make_float3(-1, -1, -1);
+    S.bmax = make_float3(1, 1, 1);
+    S.l_inv = make_float3(0.5f, 0.5f, 0.5f);
+    S.sun_dir = make_float3(0, 1, 0);
+    const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    memcpy(S.inv_view, id, sizeof(id));
+    float fovx = 54.43;                                       // K.cu:1981
+    S.cam_z    = (float)(-1.0f / tan(fovx * 0.00872664626));  // K.cu:1985, same double expression
+    S.linear   = 0;                                           // K.cu:351 (the host flips it, H.cpp:1344)
+}
+
+static void free_volume(vp_context* c)
+{
+    dev_free(c->dense);
+    dev_free(c->table);
+    dev_free(c->slot_brick);
+    dev_free(c->octets);
+    dev_free(c->bounds_voxel);
+    dev_free(c->bounds_cell);
+    dev_free(c->top);
+    dev_free(c->opacity);
+    c->n_slots = 0;
+    c->have_volume = false;
+    c->S.brick_table = nullptr;
+    c->S.octets = nullptr;
+    c->S.bounds_voxel = nullptr;
+    c->S.bounds_cell = nullptr;
+    c->S.opacity = nullptr;
+    c->S.top = nullptr;
+    c->S.have_opacity = 0;
+    c->S.julia = 0;
+}
+
+static void set_box(vp_context* c, int nx, int ny, int nz, const float* bmin, const float* bmax)
+{
+    Scene& S = c->S;
+    if (bmin && bmax)
+    {
+        S.bmin = make_float3(bmin[0], bmin[1], bmin[2]);
+        S.bmax = make_float3(bmax[0], bmax[1], bmax[2]);
+    }
+    else
+    {
+        // K.cu:373-378
+        S.bmin = make_float3(-1.0f, -(float)ny / (float)nx, -(float)nz / (float)nx);
+        S.bmax = make_float3(1.0f, (float)ny / (float)nx, (float)nz / (float)nx);
+    }
+    S.l_inv    = make_float3(1.0f / (S.bmax.x - S.bmin.x), 1.0f / (S.bmax.y - S.bmin.y), 1.0f / (S.bmax.z - S.bmin.z));  // K.cu:313
+    S.vs_scale = make_float3(S.l_inv.x * nx, S.l_inv.y * ny, S.l_inv.z * nz);
+    S.vs_off   = make_float3(-S.bmin.x * S.vs_scale.x, -S.bmin.y * S.vs_scale.y, -S.bmin.z * S.vs_scale.z);
+}
+
+// dense fp32 value volume on the device -> octet store + bound grids
+static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_voxel, int bounds_flags, int keep_dense)
+{
+    Scene& S = c->S;
+    S.nx = nx; S.ny = ny; S.nz = nz;
+    S.nbx = (nx + 1 + kBrick - 1) / kBrick; S.nby = (ny + 1 + kBrick - 1) / kBrick; S.nbz = (nz + 1 + kBrick - 1) / kBrick;
+    S.ncx = (nx + 7) >> kCellLog2; S.ncy = (ny + 7) >> kCellLog2; S.ncz = (nz + 7) >> kCellLog2;
+    S.voxel_type = store_voxel;
+    const size_t nb = (size_t)S.nbx * S.nby * S.nbz;
+    c->n_bricks     = nb;
+
+    // 1. brick classification + exclusive scan -> slots
+    uint32_t *flags = nullptr, *scan = nullptr;
+    void*     tmp   = nullptr;
+    size_t    tmp_bytes = 0;
+    VP_CUDA(cudaMalloc(&flags, nb * 4));
+    VP_CUDA(cudaMalloc(&scan, nb * 4));
+    VP_CUDA(launch_classify_bricks(c->dense, nx, ny, nz, S.nbx, S.nby, S.nbz, flags, 0));
+    VP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, scan, (int)nb, 0));
+    VP_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    VP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, scan, (int)nb, 0));
+    uint32_t last_scan = 0, last_flag = 0;
+    VP_CUDA(cudaMemcpy(&last_scan, scan + nb - 1, 4, cudaMemcpyDeviceToHost));
+    VP_CUDA(cudaMemcpy(&last_flag, flags + nb - 1, 4, cudaMemcpyDeviceToHost));
+    c->n_slots = last_scan + last_flag;
+    VP_CUDA(cudaMalloc(&c->table, nb * 4));
+    VP_CUDA(cudaMalloc(&c->slot_brick, (size_t)(c->n_slots ? c->n_slots : 1) * 4));
+    VP_CUDA(launch_make_table(flags, scan, nb, S.nbx, S.nby, c->table, c->slot_brick, 0));
+    cudaFree(tmp);
+    cudaFree(flags);
+    cudaFree(scan);
+
+    // 2. octet pool
+    const size_t ob = store_voxel == kF32 ? 32 : (store_voxel == kF16 ? 16 : 8);
+    c->octet_bytes  = (size_t)c->n_slots * kBrickCells * ob;
+    VP_CUDA(cudaMalloc(&c->octets, c->octet_bytes ? c->octet_bytes : 32));
+    VP_CUDA(launch_fill_octets(c->dense, nx, ny, nz, S.nbx, S.nby, c->slot_brick, c->n_slots, c->octets, store_voxel, 0));
+
+    // 3. bounds.  D as the reference computes it (H.cpp:1098-1101)
+    float cell_size = 2.0f / (float)nx;
+    int   D         = (int)ceil(kSearchRadius / cell_size);
+    c->bound_D      = D;
+    const size_t N  = (size_t)nx * ny * nz;
+    if (bounds_flags & VP_BOUNDS_VOXEL)
+    {
+        float2* t0 = nullptr;
+        VP_CUDA(cudaMalloc(&c->bounds_voxel, N * sizeof(float2)));
+        VP_CUDA(cudaMalloc(&t0, N * sizeof(float2)));
+        VP_CUDA(launch_bounds_axis_f32(c->dense, c->bounds_voxel, nx, ny, nz, 0, D, 1, 0));
+        VP_CUDA(launch_bounds_axis(c->bounds_voxel, t0, nx, ny, nz, 1, D, 1, 0));
+        VP_CUDA(launch_bounds_axis(t0, c->bounds_voxel, nx, ny, nz, 2, D, 1, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+        cudaFree(t0);
+    }
+    if (bounds_flags & VP_BOUNDS_CELL)
+    {
+        float2 *t0 = nullptr, *t1 = nullptr;
+        VP_CUDA(cudaMalloc(&t0, (size_t)S.ncx * ny * nz * sizeof(float2)));
+        VP_CUDA(cudaMalloc(&t1, (size_t)S.ncx * S.ncy * nz * sizeof(float2)));
+        VP_CUDA(cudaMalloc(&c->bounds_cell, (size_t)S.ncx * S.ncy * S.ncz * sizeof(float2)));
+        VP_CUDA(launch_bounds_axis_f32(c->dense, t0, nx, ny, nz, 0, D, 8, 0));
+        VP_CUDA(launch_bounds_axis(t0, t1, S.ncx, ny, nz, 1, D, 8, 0));
+        VP_CUDA(launch_bounds_axis(t1, c->bounds_cell, S.ncx, S.ncy, nz, 2, D, 8, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+        cudaFree(t0);
+        cudaFree(t1);
+    }
+    VP_CUDA(cudaDeviceSynchronize());
+    if (!keep_dense) dev_free(c->dense);
+
+    S.brick_table  = c->table;
+    S.octets       = c->octets;
+    S.bounds_voxel = c->bounds_voxel;
+    S.bounds_cell  = c->bounds_cell;
+    S.opacity      = nullptr;
+    S.have_opacity = 0;
+    S.julia        = 0;
+    c->have_volume = true;
+    return VP_OK;
+}
+
+extern "C" {
+
+const char* vp_last_error(void) { return g_err; }
+const char* vp_version(void) { return "volpath-b200 0.1 (sm_100a)"; }
+
+int vp_create(int device, vp_context** out)
+{
+    if (!out) return fail(VP_ERR_INVALID, "vp_create: null out");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail(VP_ERR_NO_DEVICE, "vp_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(VP_ERR_INVALID, "vp_create: device %d out of range (%d devices)", device, n);
+    VP_CUDA(cudaSetDevice(device));
+    vp_context* c = new (std::nothrow) vp_context();
+    if (!c) return fail(VP_ERR_INVALID, "vp_create: out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    VP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    scene_defaults(c->S);
+    const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    memcpy(c->inv_model, id, sizeof(id));
+    VP_CUDA(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    VP_CUDA(cudaEventCreate(&c->ev0));
+    VP_CUDA(cudaEventCreate(&c->ev1));
+    // a 1x1 black environment until init_envmap is called
+    VP_CUDA(cudaMalloc(&c->env, sizeof(float4)));
+    VP_CUDA(cudaMemset(c->env, 0, sizeof(float4)));
+    c->S.env = c->env; c->S.env_w = 1; c->S.env_h = 1;
+    *out = c;
+    return VP_OK;
+}
+
+int vp_destroy(vp_context* c)
+{
+    if (!c) return VP_OK;
+    cudaSetDevice(c->device);
+    free_volume(c);
+    dev_free(c->env);
+    dev_free(c->d_stats);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return VP_OK;
+}
+
+int vp_free_volume(vp_context* c)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    VP_CUDA(cudaSetDevice(c->device));
+    free_volume(c);
+    return VP_OK;
+}
+
+int vp_upload_volume(vp_context* c, const void* volume, int nx, int ny, int nz, int src_voxel, int store_voxel, int memspace,
+                     const float* boxmin3, const float* boxmax3, int bounds_flags)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    if (!volume) return fail(VP_ERR_NO_VOLUME, "cannot init without host volume");  // K.cu:360-364 (the reference exits)
+    if (nx < 1 || ny < 1 || nz < 1 || nx > 8184 || ny > 8184 || nz > 8184) return fail(VP_ERR_INVALID, "bad volume dims %d %d %d", nx, ny, nz);
+    if (src_voxel != VP_VOXEL_U8 && src_voxel != VP_VOXEL_F32) return fail(VP_ERR_UNSUPPORTED, "source voxels must be u8 or f32");
+    if (store_voxel < VP_VOXEL_U8 || store_voxel > VP_VOXEL_F32) return fail(VP_ERR_INVALID, "bad store voxel type");
+    if (!(bounds_flags & (VP_BOUNDS_VOXEL | VP_BOUNDS_CELL))) return fail(VP_ERR_INVALID, "bounds_flags selects no bound grid");
+    VP_CUDA(cudaSetDevice(c->device));
+    free_volume(c);
+    const size_t N = (size_t)nx * ny * nz;
+    VP_CUDA(cudaMalloc(&c->dense, N * sizeof(float)));
+    const cudaMemcpyKind kind = memspace == VP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (src_voxel == VP_VOXEL_F32)
+    {
+        VP_CUDA(cudaMemcpy(c->dense, volume, N * sizeof(float), kind));
+    }
+    else
+    {
+        uint8_t* d8 = nullptr;
+        VP_CUDA(cudaMalloc(&d8, N));
+        VP_CUDA(cudaMemcpy(d8, volume, N, kind));
+        VP_CUDA(launch_u8_to_f32(d8, c->dense, N, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+        cudaFree(d8);
+    }
+    set_box(c, nx, ny, nz, boxmin3, boxmax3);
+    return build_from_dense(c, nx, ny, nz, store_voxel, bounds_flags, 0);
+}
+
+int vp_generate_cloud(vp_context* c, int nx, int ny, int nz, unsigned int seed, int store_voxel, const float* boxmin3,
+                      const float* boxmax3, int bounds_flags, int keep_dense)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    if (nx < 1 || ny < 1 || nz < 1 || nx > 8184 || ny > 8184 || nz > 8184) return fail(VP_ERR_INVALID, "bad volume dims %d %d %d", nx, ny, nz);
+    if (store_voxel < VP_VOXEL_U8 || store_voxel > VP_VOXEL_F32) return fail(VP_ERR_INVALID, "bad store voxel type");
+    if (!(bounds_flags & (VP_BOUNDS_VOXEL | VP_BOUNDS_CELL))) return fail(VP_ERR_INVALID, "bounds_flags selects no bound grid");
+    VP_CUDA(cudaSetDevice(c->device));
+    free_volume(c);
+    const size_t N = (size_t)nx * ny * nz;
+    VP_CUDA(cudaMalloc(&c->dense, N * sizeof(float)));
+    VP_CUDA(launch_fbm_cloud(c->dense, nx, ny, nz, seed, 0));
+    set_box(c, nx, ny, nz, boxmin3, boxmax3);
+    return build_from_dense(c, nx, ny, nz, store_voxel, bounds_flags, keep_dense);
+}
+
+const void* vp_dense_volume(vp_context* c) { return c ? c->dense : nullptr; }
+int         vp_release_dense(vp_context* c)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    dev_free(c->dense);
+    return VP_OK;
+}
+
+int vp_set_julia(vp_context* c)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    VP_CUDA(cudaSetDevice(c->device));
+    free_volume(c);
+    Scene& S = c->S;
+    S.nx = S.ny = S.nz = 32;  // H.cpp:1346 (extent only; the density is procedural)
+    set_box(c, 1, 1, 1, nullptr, nullptr);
+    S.julia        = 1;
+    c->have_volume = true;
+    return VP_OK;
+}
+
+int vp_set_filter(vp_context* c, int linear)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    c->S.linear = linear ? 1 : 0;
+    return VP_OK;
+}
+
+int vp_set_envmap(vp_context* c, const float* rgba, int width, int height)
+{
+    if (!c || !rgba || width < 1 || height < 1) return fail(VP_ERR_INVALID, "vp_set_envmap: bad arguments");
+    VP_CUDA(cudaSetDevice(c->device));
+    dev_free(c->env);
+    VP_CUDA(cudaMalloc(&c->env, (size_t)width * height * sizeof(float4)));
+    VP_CUDA(cudaMemcpy(c->env, rgba, (size_t)width * height * sizeof(float4), cudaMemcpyHostToDevice));
+    c->S.env = c->env; c->S.env_w = width; c->S.env_h = height;
+    return VP_OK;
+}
+
+int vp_set_sun(vp_context* c, const float* dir3, const float* power3)
+{
+    if (!c || !dir3 || !power3) return fail(VP_ERR_INVALID, "vp_set_sun: bad arguments");
+    // K.cu:1269-1283: disk radiance -> directional power, r = 0.45/94 (float)(double/float)
+    Scene& S = c->S;
+    S.sun_power_original = make_float3(power3[0], power3[1], power3[2]);
+    float r     = (float)(0.45 / 94.0f);
+    float scale = kPi * (r * r);
+    S.sun_power = make_float3(S.sun_power_original.x * scale, S.sun_power_original.y * scale, S.sun_power_original.z * scale);
+    S.sun_dir   = make_float3(dir3[0], dir3[1], dir3[2]);
+    return VP_OK;
+}
+
+int vp_set_inv_view(vp_context* c, const float* m12)
+{
+    if (!c || !m12) return fail(VP_ERR_INVALID, "vp_set_inv_view: bad arguments");
+    memcpy(c->S.inv_view, m12, 12 * sizeof(float));
+    return VP_OK;
+}
+
+int vp_precompute_opacity(vp_context* c, const float* dir3)
+{
+    if (!c || !dir3) return fail(VP_ERR_INVALID, "vp_precompute_opacity: bad arguments");
+    if (!c->have_volume) return fail(VP_ERR_NO_VOLUME, "vp_precompute_opacity: no volume");
+    VP_CUDA(cudaSetDevice(c->device));
+    if (c->S.julia) return VP_OK;  // the table of the no-OpenVDB build is built from a zero density
+    dev_free(c->opacity);
+    c->S.have_opacity = 0;
+    c->S.opacity      = nullptr;
+    VP_CUDA(cudaMalloc(&c->opacity, (size_t)(c->n_slots ? c->n_slots : 1) * kOpBrickPad * sizeof(float)));
+    VP_CUDA(launch_precompute_opacity(c->S, c->slot_brick, c->n_slots, c->opacity, make_float3(dir3[0], dir3[1], dir3[2]), 0));
+    c->launches++;
+    VP_CUDA(cudaDeviceSynchronize());
+    c->S.opacity      = c->opacity;
+    c->S.have_opacity = 1;
+    return VP_OK;
+}
+
+int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
+              vp_stream stream)
+{
+    if (!c || !d_sum || !p) return fail(VP_ERR_INVALID, "vp_render: bad arguments");
+    if (!c->have_volume) return fail(VP_ERR_NO_VOLUME, "vp_render: no volume uploaded");
+    if (n_frames <= 0) return VP_OK;
+    if (p->width == 0 || p->height == 0 || p->width > 65535 || p->height > 65535) return fail(VP_ERR_INVALID, "vp_render: bad image size");
+    VP_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    VP_CUDA(cudaEventRecord(c->ev0, st));
+    if (mode == VP_MODE_PARITY)
+    {
+        if (!c->S.julia && !c->S.bounds_voxel) return fail(VP_ERR_INVALID, "vp_render: parity mode needs VP_BOUNDS_VOXEL");
+        VP_CUDA(launch_render_parity(c->S, (float4*)d_sum, first_frame, n_frames, frame_stride, *p, st));
+        c->launches++;
+    }
+    else if (mode == VP_MODE_FAST)
+    {
+        // <= 512 frames per launch keeps the item counter and the per-CTA run time bounded
+        for (int f = 0; f < n_frames; f += 512)
+        {
+            int nf = n_frames - f < 512 ? n_frames - f : 512;
+            VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + f * frame_stride, nf, frame_stride, *p,
+                                       c->stats_on ? c->d_stats : nullptr, st));
+            c->launches++;
+        }
+    }
+    else
+        return fail(VP_ERR_INVALID, "vp_render: unknown mode %d", mode);
+    VP_CUDA(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    return VP_OK;
+}
+
+int vp_resolve(vp_context* c, void* dst, const void* src, int size, float scale, float gamma, vp_stream stream)
+{
+    if (!c || !dst || !src) return fail(VP_ERR_INVALID, "vp_resolve: bad arguments");
+    VP_CUDA(cudaSetDevice(c->device));
+    VP_CUDA(launch_resolve((float4*)dst, (const float4*)src, size, scale, gamma, (cudaStream_t)stream));
+    c->launches++;
+    return VP_OK;
+}
+
+int vp_render_to_host(vp_context* c, void* h_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode)
+{
+    if (!c || !h_sum || !p) return fail(VP_ERR_INVALID, "vp_render_to_host: bad arguments");
+    VP_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)p->width * p->height * sizeof(float4);
+    float4*      d     = nullptr;
+    VP_CUDA(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpy(d, h_sum, bytes, cudaMemcpyHostToDevice);
+    int         r = e == cudaSuccess ? vp_render(c, d, first_frame, n_frames, frame_stride, p, mode, nullptr) : (int)e;
+    if (r == 0) e = cudaMemcpy(h_sum, d, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (r != 0) return r;
+    VP_CUDA(e);
+    return VP_OK;
+}
+
+int vp_sync(vp_context* c)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    VP_CUDA(cudaSetDevice(c->device));
+    VP_CUDA(cudaDeviceSynchronize());
+    return VP_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------------
+int vp_get_bounds_voxel(vp_context* c, float* h_out)
+{
+    if (!c || !c->bounds_voxel) return fail(VP_ERR_INVALID, "no per-voxel bounds");
+    VP_CUDA(cudaMemcpy(h_out, c->bounds_voxel, (size_t)c->S.nx * c->S.ny * c->S.nz * sizeof(float2), cudaMemcpyDeviceToHost));
+    return VP_OK;
+}
+int vp_get_bounds_cell(vp_context* c, float* h_out, int* dims3)
+{
+    if (!c || !c->bounds_cell) return fail(VP_ERR_INVALID, "no per-cell bounds");
+    if (dims3) { dims3[0] = c->S.ncx; dims3[1] = c->S.ncy; dims3[2] = c->S.ncz; }
+    if (h_out)
+        VP_CUDA(cudaMemcpy(h_out, c->bounds_cell, (size_t)c->S.ncx * c->S.ncy * c->S.ncz * sizeof(float2), cudaMemcpyDeviceToHost));
+    return VP_OK;
+}
+int vp_get_opacity(vp_context* c, float* h_out)
+{
+    if (!c || !c->opacity) return fail(VP_ERR_INVALID, "no opacity table");
+    size_t N = (size_t)c->S.nx * c->S.ny * c->S.nz;
+    float* d = nullptr;
+    VP_CUDA(cudaMalloc(&d, N * sizeof(float)));
+    VP_CUDA(launch_gather_opacity(c->S, d, 0));
+    cudaError_t e = cudaMemcpy(h_out, d, N * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    VP_CUDA(e);
+    return VP_OK;
+}
+int vp_fetch_density(vp_context* c, const float* h_pos3, int n, int parity_filter, float* h_out)
+{
+    if (!c || !c->have_volume || c->S.julia) return fail(VP_ERR_NO_VOLUME, "vp_fetch_density: no stored volume");
+    float3* dp = nullptr;
+    float*  dv = nullptr;
+    VP_CUDA(cudaMalloc(&dp, (size_t)n * sizeof(float3)));
+    VP_CUDA(cudaMalloc(&dv, (size_t)n * sizeof(float)));
+    VP_CUDA(cudaMemcpy(dp, h_pos3, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice));
+    VP_CUDA(launch_fetch_density(c->S, dp, n, parity_filter, dv, 0));
+    cudaError_t e = cudaMemcpy(h_out, dv, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dp);
+    cudaFree(dv);
+    VP_CUDA(e);
+    return VP_OK;
+}
+int vp_volume_stats(vp_context* c, unsigned long long* out8)
+{
+    if (!c || !out8) return fail(VP_ERR_INVALID, "bad arguments");
+    out8[0] = c->n_bricks;
+    out8[1] = c->n_slots;
+    out8[2] = c->octet_bytes;
+    out8[3] = (unsigned long long)c->bound_D;
+    out8[4] = c->bounds_cell ? (unsigned long long)c->S.ncx * c->S.ncy * c->S.ncz * sizeof(float2) : 0;
+    out8[5] = c->bounds_voxel ? (unsigned long long)c->S.nx * c->S.ny * c->S.nz * sizeof(float2) : 0;
+    out8[6] = c->opacity ? (unsigned long long)c->n_slots * kOpBrickPad * sizeof(float) : 0;
+    out8[7] = (unsigned long long)c->n_bricks * 4;
+    return VP_OK;
+}
+int vp_rng_sequence(vp_context* c, unsigned int x, unsigned int y, unsigned int frame, int n, float* h_out_f, unsigned int* h_out_u)
+{
+    if (!c || n < 1) return fail(VP_ERR_INVALID, "bad arguments");
+    float*    df = nullptr;
+    uint32_t* du = nullptr;
+    VP_CUDA(cudaMalloc(&df, (size_t)n * 4));
+    VP_CUDA(cudaMalloc(&du, (size_t)n * 4));
+    VP_CUDA(launch_rng_sequence(x, y, frame, n, df, du, 0));
+    cudaError_t e = cudaSuccess;
+    if (h_out_f) e = cudaMemcpy(h_out_f, df, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (h_out_u && e == cudaSuccess) e = cudaMemcpy(h_out_u, du, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(df);
+    cudaFree(du);
+    VP_CUDA(e);
+    return VP_OK;
+}
+int vp_philox2x32(vp_context* c, unsigned int c0, unsigned int c1, unsigned int key, unsigned int* h_out2)
+{
+    if (!c || !h_out2) return fail(VP_ERR_INVALID, "bad arguments");
+    uint32_t* d = nullptr;
+    VP_CUDA(cudaMalloc(&d, 8));
+    VP_CUDA(launch_philox(c0, c1, key, d, 0));
+    cudaError_t e = cudaMemcpy(h_out2, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    VP_CUDA(e);
+    return VP_OK;
+}
+int vp_set_stats(vp_context* c, int enable)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    c->stats_on = enable != 0;
+    return VP_OK;
+}
+int vp_render_counters(vp_context* c, unsigned long long* out8, int reset)
+{
+    if (!c || !out8) return fail(VP_ERR_INVALID, "bad arguments");
+    VP_CUDA(cudaDeviceSynchronize());
+    VP_CUDA(cudaMemcpy(out8, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) VP_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    return VP_OK;
+}
+int vp_last_kernel_ms(vp_context* c, float* ms)
+{
+    if (!c || !ms || !c->timed) return fail(VP_ERR_INVALID, "no timed render");
+    VP_CUDA(cudaEventSynchronize(c->ev1));
+    VP_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return VP_OK;
+}
+int vp_launch_count(vp_context* c, unsigned long long* n)
+{
+    if (!c || !n) return fail(VP_ERR_INVALID, "bad arguments");
+    *n = c->launches;
+    return VP_OK;
+}
+
+// plain device-memory helpers for C / ctypes callers that have no CUDA runtime of their own
+void* vp_dev_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, bytes);
+    return p;
+}
+int vp_dev_free(void* p) { return (int)cudaFree(p); }
+int vp_dev_zero(void* p, size_t bytes) { return (int)cudaMemset(p, 0, bytes); }
+int vp_dev_to_host(void* h, const void* d, size_t bytes) { return (int)cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost); }
+int vp_host_to_dev(void* d, const void* h, size_t bytes) { return (int)cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); }
+
+// =======================================================================================================
+// (1) reference-named shims over one implicit context on the current device
+// =======================================================================================================
+static vp_context* g_shim      = nullptr;
+static int         g_shim_mode = VP_MODE_PARITY;
+
+vp_context* vp_shim_context(void)
+{
+    if (!g_shim)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (vp_create(dev, &g_shim) != VP_OK)
+        {
+            fprintf(stderr, "volpath: %s\n", g_err);
+            return nullptr;
+        }
+    }
+    return g_shim;
+}
+void vp_shim_set_mode(int mode) { g_shim_mode = mode; }
+
+#define SHIM_CTX()                         \
+    vp_context* c = vp_shim_context();     \
+    if (!c) return
+#define SHIM_REPORT(call)                                              \
+    do {                                                               \
+        if ((call) != VP_OK) fprintf(stderr, "volpath: %s\n", g_err);  \
+    } while (0)
+
+void init_cuda(void* h_volume, vp_extent volumeSize, bool quantized, const vp_float3* boxmin, const vp_float3* boxmax)
+{
+    SHIM_CTX();
+    const float* lo = (boxmin && boxmax) ? &boxmin->x : nullptr;
+    const float* hi = (boxmin && boxmax) ? &boxmax->x : nullptr;
+    // the filter mode survives re-initialisation like the reference's file-scope `linear_interp` (K.cu:351)
+    SHIM_REPORT(vp_upload_volume(c, h_volume, (int)volumeSize.width, (int)volumeSize.height, (int)volumeSize.depth,
+                                 quantized ? VP_VOXEL_U8 : VP_VOXEL_F32, quantized ? VP_VOXEL_U8 : VP_VOXEL_F32, VP_MEM_HOST, lo, hi,
+                                 VP_BOUNDS_VOXEL | VP_BOUNDS_CELL));
+}
+void set_texture_filter_mode(bool bLinearFilter)
+{
+    SHIM_CTX();
+    vp_set_filter(c, bLinearFilter ? 1 : 0);
+}
+void free_cuda_buffers(void)
+{
+    SHIM_CTX();
+    vp_free_volume(c);
+}
+void precompute_opacity(const float* light_dir)
+{
+    SHIM_CTX();
+    SHIM_REPORT(vp_precompute_opacity(c, light_dir));
+}
+void init_envmap(const vp_float4* HDRmap, int width, int height)
+{
+    SHIM_CTX();
+    SHIM_REPORT(vp_set_envmap(c, &HDRmap->x, width, height));
+}
+void free_envmap(void) {}
+void set_sun(float* sun_dir, float* sun_power)
+{
+    SHIM_CTX();
+    SHIM_REPORT(vp_set_sun(c, sun_dir, sun_power));
+}
+void copy_inv_view_matrix(float* invViewMatrix, size_t sizeofMatrix)
+{
+    SHIM_CTX();
+    float m[12];
+    memcpy(m, c->S.inv_view, sizeof(m));
+    memcpy(m, invViewMatrix, sizeofMatrix < sizeof(m) ? sizeofMatrix : sizeof(m));
+    vp_set_inv_view(c, m);
+}
+void copy_inv_model_matrix(float* invModelMatrix, size_t sizeofMatrix)
+{
+    SHIM_CTX();
+    memcpy(c->inv_model, invModelMatrix, sizeofMatrix < sizeof(c->inv_model) ? sizeofMatrix : sizeof(c->inv_model));
+}
+void init_rng(vp_dim3, vp_dim3, int, int) {}
+void free_rng(void) {}
+void scale(vp_float4* dst, vp_float4* src, int size, float scale_)
+{
+    SHIM_CTX();
+    SHIM_REPORT(vp_resolve(c, dst, src, size, scale_, 0.0f, nullptr));
+}
+void gamma_correct(vp_float4* dst, vp_float4* src, int size, float scale_, float gamma)
+{
+    SHIM_CTX();
+    SHIM_REPORT(vp_resolve(c, dst, src, size, scale_, gamma, nullptr));
+}
+void render_kernel(vp_dim3, vp_dim3, vp_float4* d_output, int spp, const vp_param* p)
+{
+    SHIM_CTX();
+    SHIM_REPORT(vp_render(c, d_output, spp, 1, 1, p, g_shim_mode, nullptr));
+}
+
+}  // extern "C"

@@ -1,0 +1,485 @@
+// volpath_build.cu -- scene-build kernels: everything vp_upload_volume / vp_generate_cloud /
+// vp_precompute_opacity run once per volume or sun change (the B200 replacement of init_cuda's
+// cudaArray upload + CPU bound sweep, K.cu:354-420 / H.cpp:1089-1267, and of _precompute_opacity,
+// K.cu:483-524).  All of it is HBM-bound byte/compare work: coalesced along x, no tensor cores.
+#include "volpath_common.cuh"
+#include "volpath_kernels.h"
+
+namespace vp
+{
+static inline unsigned int grid_for(size_t n, int block, size_t cap = (size_t)148 * 64)
+{
+    size_t g = (n + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned int)g;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// synthetic fBm cloud.  Bit-identical to oracle vo_fbm_cloud_f32: all lattice
+// arithmetic is integer; the few float operations are single IEEE operations (__f*_rn: no contraction).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rotl13(uint32_t h) { return __funnelshift_l(h, h, 13); }
+__device__ __forceinline__ uint32_t lattice_hash(uint32_t x, uint32_t y, uint32_t z, uint32_t seed)
+{
+    uint32_t h = seed;
+    h ^= x * 0x8da6b343u; h = rotl13(h); h *= 0x9e3779b1u;
+    h ^= y * 0xd8163841u; h = rotl13(h); h *= 0x9e3779b1u;
+    h ^= z * 0xcb1ab31fu; h = rotl13(h); h *= 0x9e3779b1u;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t smooth_fx(uint32_t t)
+{
+    uint64_t t2 = ((uint64_t)t * t) >> 16;
+    uint64_t r  = (t2 * (3u * 65536u - 2u * t)) >> 16;
+    return (uint32_t)(r > 65535u ? 65535u : r);
+}
+__device__ __forceinline__ uint64_t lerp_fx(uint64_t a, uint64_t b, uint32_t w) { return (a * (65536u - w) + b * w) >> 16; }
+__device__ uint32_t value_noise_fx(uint32_t px, uint32_t py, uint32_t pz, uint32_t seed)
+{
+    uint32_t ix = px >> 16, iy = py >> 16, iz = pz >> 16;
+    uint32_t wx = smooth_fx(px & 0xffffu), wy = smooth_fx(py & 0xffffu), wz = smooth_fx(pz & 0xffffu);
+    uint64_t l000 = lattice_hash(ix, iy, iz, seed) & 0xffffu, l100 = lattice_hash(ix + 1, iy, iz, seed) & 0xffffu;
+    uint64_t l010 = lattice_hash(ix, iy + 1, iz, seed) & 0xffffu, l110 = lattice_hash(ix + 1, iy + 1, iz, seed) & 0xffffu;
+    uint64_t l001 = lattice_hash(ix, iy, iz + 1, seed) & 0xffffu, l101 = lattice_hash(ix + 1, iy, iz + 1, seed) & 0xffffu;
+    uint64_t l011 = lattice_hash(ix, iy + 1, iz + 1, seed) & 0xffffu, l111 = lattice_hash(ix + 1, iy + 1, iz + 1, seed) & 0xffffu;
+    uint64_t x00 = lerp_fx(l000, l100, wx), x10 = lerp_fx(l010, l110, wx);
+    uint64_t x01 = lerp_fx(l001, l101, wx), x11 = lerp_fx(l011, l111, wx);
+    uint64_t y0 = lerp_fx(x00, x10, wy), y1 = lerp_fx(x01, x11, wy);
+    return (uint32_t)lerp_fx(y0, y1, wz);
+}
+__device__ float fbm_cloud_voxel(int i, int j, int k, int nx, int ny, int nz, uint32_t seed)
+{
+    int      nmax = max(nx, max(ny, nz));
+    uint64_t sum  = 0;
+#pragma unroll 1
+    for (int o = 0; o < 5; o++)
+    {
+        uint64_t f  = (uint64_t)3 << o;
+        uint32_t px = (uint32_t)((((uint64_t)(2 * i + 1) * f) << 15) / (uint64_t)nmax);
+        uint32_t py = (uint32_t)((((uint64_t)(2 * j + 1) * f) << 15) / (uint64_t)nmax);
+        uint32_t pz = (uint32_t)((((uint64_t)(2 * k + 1) * f) << 15) / (uint64_t)nmax);
+        sum += (uint64_t)value_noise_fx(px, py, pz, seed + 1234u + (uint32_t)o) << (4 - o);
+    }
+    float n  = __fdiv_rn((float)sum, (float)(65535u * 31u));
+    float ux = __fsub_rn(__fdiv_rn((float)(2 * i + 1), (float)nx), 1.0f);
+    float uy = __fsub_rn(__fdiv_rn((float)(2 * j + 1), (float)ny), 1.0f);
+    float uz = __fsub_rn(__fdiv_rn((float)(2 * k + 1), (float)nz), 1.0f);
+    float r2 = __fmul_rn(ux, ux);
+    r2       = __fadd_rn(r2, __fmul_rn(uy, uy));
+    r2       = __fadd_rn(r2, __fmul_rn(uz, uz));
+    float fall = __fsub_rn(1.0f, r2);
+    float base = __fmul_rn(__fadd_rn(uy, 0.75f), 4.0f);
+    base       = base < 0.0f ? 0.0f : (base > 1.0f ? 1.0f : base);
+    float v    = __fadd_rn(n, __fmul_rn(fall, 0.7f));
+    v          = __fsub_rn(v, 0.76f);
+    v          = __fmul_rn(v, 3.0f);
+    v          = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+    return __fmul_rn(v, base);
+}
+__global__ void __launch_bounds__(256) k_fbm_cloud(float* __restrict__ out, int nx, int ny, int nz, uint32_t seed)
+{
+    size_t rows = (size_t)ny * nz;
+    for (size_t row = blockIdx.x; row < rows; row += gridDim.x)
+    {
+        int j = (int)(row % ny), k = (int)(row / ny);
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) out[row * nx + i] = fbm_cloud_voxel(i, j, k, nx, ny, nz, seed);
+    }
+}
+cudaError_t launch_fbm_cloud(float* d_dense, int nx, int ny, int nz, uint32_t seed, cudaStream_t stream)
+{
+    size_t rows = (size_t)ny * nz;
+    k_fbm_cloud<<<(unsigned int)(rows < 148u * 256u ? rows : 148u * 256u), 256, 0, stream>>>(d_dense, nx, ny, nz, seed);
+    return cudaGetLastError();
+}
+
+// u8 -> the float the reference's normalised-float texture read returns (K.cu:247, 261): v / 255
+__global__ void __launch_bounds__(256) k_u8_to_f32(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __fdiv_rn((float)src[i], 255.0f);
+}
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t stream)
+{
+    k_u8_to_f32<<<grid_for(n, 256), 256, 0, stream>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// local (max,min) bounds: the reference's per-voxel clamped +-D cube (H.cpp:1089-1267) as three separable
+// sliding-window sweeps.  max/min are exact, so any evaluation order is bit-identical to the reference's
+// monotonic-deque sweeps.  `cell` > 1 additionally reduces the swept axis by that factor: output c covers
+// inputs [c*cell - D, c*cell + cell - 1 + D] (clamped) -- the per-cell bound grid of the fast renderer.
+// ---------------------------------------------------------------------------------------------------
+template <class TIn>
+__device__ __forceinline__ float2 as_pair(TIn v);
+template <>
+__device__ __forceinline__ float2 as_pair<float>(float v) { return make_float2(v, v); }
+template <>
+__device__ __forceinline__ float2 as_pair<float2>(float2 v) { return v; }
+
+template <class TIn>
+__global__ void __launch_bounds__(256) k_bounds_axis(const TIn* __restrict__ in, float2* __restrict__ out, int n0, int n1,
+                                                      int n2, int axis, int D, int cell)
+{
+    const int n_axis = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+    const int m_axis = (n_axis + cell - 1) / cell;
+    const int m0 = axis == 0 ? m_axis : n0, m1 = axis == 1 ? m_axis : n1, m2 = axis == 2 ? m_axis : n2;
+    const size_t total  = (size_t)m0 * m1 * m2;
+    const size_t stride = axis == 0 ? 1 : (axis == 1 ? (size_t)n0 : (size_t)n0 * n1);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        int    i0 = (int)(idx % m0), i1 = (int)((idx / m0) % m1), i2 = (int)(idx / ((size_t)m0 * m1));
+        int    c  = axis == 0 ? i0 : (axis == 1 ? i1 : i2);
+        int    lo = max(0, c * cell - D), hi = min(n_axis - 1, c * cell + cell - 1 + D);
+        size_t base = axis == 0 ? ((size_t)i2 * n1 + i1) * n0 : (axis == 1 ? (size_t)i2 * n1 * n0 + i0 : (size_t)i1 * n0 + i0);
+        float2 r = as_pair<TIn>(in[base + (size_t)lo * stride]);
+        for (int t = lo + 1; t <= hi; t++)
+        {
+            float2 v = as_pair<TIn>(in[base + (size_t)t * stride]);
+            r.x      = v.x > r.x ? v.x : r.x;
+            r.y      = v.y < r.y ? v.y : r.y;
+        }
+        out[idx] = r;
+    }
+}
+cudaError_t launch_bounds_axis_f32(const float* in, float2* out, int n0, int n1, int n2, int axis, int D, int cell,
+                                   cudaStream_t stream)
+{
+    int    na    = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+    size_t total = (size_t)n0 * n1 * n2 / na * ((na + cell - 1) / cell);
+    k_bounds_axis<float><<<grid_for(total, 256, (size_t)148 * 256), 256, 0, stream>>>(in, out, n0, n1, n2, axis, D, cell);
+    return cudaGetLastError();
+}
+cudaError_t launch_bounds_axis(const float2* in, float2* out, int n0, int n1, int n2, int axis, int D, int cell,
+                               cudaStream_t stream)
+{
+    int    na    = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+    size_t total = (size_t)n0 * n1 * n2 / na * ((na + cell - 1) / cell);
+    k_bounds_axis<float2><<<grid_for(total, 256, (size_t)148 * 256), 256, 0, stream>>>(in, out, n0, n1, n2, axis, D, cell);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// octet store build.  Brick (bx,by,bz) holds cells' c = 8b .. 8b+7 per axis; cell' c has corner voxels
+// c-1 and c (clamped to [0, N-1]) -- so a brick touches voxels 8b-1 .. 8b+7.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_classify_bricks(const float* __restrict__ dense, int nx, int ny, int nz, int nbx,
+                                                          int nby, int nbz, uint32_t* __restrict__ flags)
+{
+    // one warp per brick; 9^3 = 729 voxels
+    const int    lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
+    const size_t nb   = (size_t)nbx * nby * nbz;
+    for (size_t b = (size_t)blockIdx.x * 4 + warp_in_block; b < nb; b += (size_t)gridDim.x * 4)
+    {
+        int  bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((size_t)nbx * nby));
+        bool any = false;
+        for (int t = lane; t < 729 && !any; t += 32)
+        {
+            int lx = t % 9, ly = (t / 9) % 9, lz = t / 81;
+            int i = clampi(bx * 8 - 1 + lx, 0, nx - 1), j = clampi(by * 8 - 1 + ly, 0, ny - 1), k = clampi(bz * 8 - 1 + lz, 0, nz - 1);
+            any = dense[((size_t)k * ny + j) * nx + i] != 0.0f;
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (lane == 0) flags[b] = any ? 1u : 0u;
+    }
+}
+cudaError_t launch_classify_bricks(const float* dense, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* flags,
+                                   cudaStream_t stream)
+{
+    size_t nb = (size_t)nbx * nby * nbz;
+    k_classify_bricks<<<grid_for((nb + 3) / 4, 1, (size_t)148 * 64), 128, 0, stream>>>(dense, nx, ny, nz, nbx, nby, nbz, flags);
+    return cudaGetLastError();
+}
+
+// flags + exclusive scan -> brick table (slot or kEmptyBrick) and the slot -> brick coordinate list
+__global__ void __launch_bounds__(256) k_make_table(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan,
+                                                     size_t nb, int nbx, int nby, uint32_t* __restrict__ table,
+                                                     uint32_t* __restrict__ slot_brick)
+{
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x)
+    {
+        if (flags[b])
+        {
+            uint32_t s = scan[b];
+            table[b]   = s;
+            if (slot_brick) slot_brick[s] = (uint32_t)b;
+        }
+        else
+            table[b] = kEmptyBrick;
+    }
+}
+cudaError_t launch_make_table(const uint32_t* flags, const uint32_t* scan, size_t nb, int nbx, int nby, uint32_t* table,
+                              uint32_t* slot_brick, cudaStream_t stream)
+{
+    k_make_table<<<grid_for(nb, 256), 256, 0, stream>>>(flags, scan, nb, nbx, nby, table, slot_brick);
+    return cudaGetLastError();
+}
+
+template <int VT>
+__global__ void __launch_bounds__(256) k_fill_octets(const float* __restrict__ dense, int nx, int ny, int nz, int nbx, int nby,
+                                                      const uint32_t* __restrict__ slot_brick, uint32_t n_slots,
+                                                      void* __restrict__ pool)
+{
+    __shared__ float tile[729];
+    for (uint32_t s = blockIdx.x; s < n_slots; s += gridDim.x)
+    {
+        uint32_t b  = slot_brick[s];
+        int      bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((uint32_t)nbx * nby));
+        __syncthreads();
+        for (int t = threadIdx.x; t < 729; t += blockDim.x)
+        {
+            int lx = t % 9, ly = (t / 9) % 9, lz = t / 81;
+            int i = clampi(bx * 8 - 1 + lx, 0, nx - 1), j = clampi(by * 8 - 1 + ly, 0, ny - 1), k = clampi(bz * 8 - 1 + lz, 0, nz - 1);
+            tile[t] = dense[((size_t)k * ny + j) * nx + i];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < kBrickCells; c += blockDim.x)
+        {
+            int   cx = c & 7, cy = (c >> 3) & 7, cz = c >> 6;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = tile[((cz + (q >> 2)) * 9 + cy + ((q >> 1) & 1)) * 9 + cx + (q & 1)];
+            size_t cell = (size_t)s * kBrickCells + c;
+            if (VT == kF32)
+            {
+                float4* p = reinterpret_cast<float4*>(pool) + cell * 2;
+                p[0]      = make_float4(v[0], v[1], v[2], v[3]);
+                p[1]      = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            else if (VT == kF16)
+            {
+                __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+                uint4   u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                reinterpret_cast<uint4*>(pool)[cell] = u;
+            }
+            else
+            {
+                // the dense copy of a u8 source holds k/255 (correctly rounded): k = rint(v*255) is exact
+                uint32_t q[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) q[t] = (uint32_t)__float2int_rn(fminf(fmaxf(v[t], 0.0f), 1.0f) * 255.0f);
+                uint2 u;
+                u.x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+                u.y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+                reinterpret_cast<uint2*>(pool)[cell] = u;
+            }
+        }
+    }
+}
+cudaError_t launch_fill_octets(const float* dense, int nx, int ny, int nz, int nbx, int nby, const uint32_t* slot_brick,
+                               uint32_t n_slots, void* pool, int voxel_type, cudaStream_t stream)
+{
+    if (n_slots == 0) return cudaSuccess;
+    unsigned int g = n_slots < 148u * 32u ? n_slots : 148u * 32u;
+    if (voxel_type == kF32)
+        k_fill_octets<kF32><<<g, 256, 0, stream>>>(dense, nx, ny, nz, nbx, nby, slot_brick, n_slots, pool);
+    else if (voxel_type == kF16)
+        k_fill_octets<kF16><<<g, 256, 0, stream>>>(dense, nx, ny, nz, nbx, nby, slot_brick, n_slots, pool);
+    else
+        k_fill_octets<kU8><<<g, 256, 0, stream>>>(dense, nx, ny, nz, nbx, nby, slot_brick, n_slots, pool);
+    return cudaGetLastError();
+}
+
+// top-level occupancy: one byte per (cells_per_top)^3 block of bound cells, 1 if any cell's max > 0.
+// Because a bound cell's max covers the cell +-D voxels, top == 0 means the density is zero within D voxels
+// (>= search_radius) of every point of the block: whole 0.05-segments starting there see no medium.
+__global__ void __launch_bounds__(256) k_top_grid(const float2* __restrict__ bounds_cell, int ncx, int ncy, int ncz,
+                                                   uint8_t* __restrict__ top, int tx, int ty, int tz, int cpt)
+{
+    size_t total = (size_t)tx * ty * tz;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        int  ix = (int)(idx % tx), iy = (int)((idx / tx) % ty), iz = (int)(idx / ((size_t)tx * ty));
+        bool any = false;
+        for (int k = iz * cpt; k < min(ncz, iz * cpt + cpt) && !any; k++)
+            for (int j = iy * cpt; j < min(ncy, iy * cpt + cpt) && !any; j++)
+                for (int i = ix * cpt; i < min(ncx, ix * cpt + cpt); i++)
+                    if (bounds_cell[((size_t)k * ncy + j) * ncx + i].x > 0.0f)
+                    {
+                        any = true;
+                        break;
+                    }
+        top[idx] = any ? 1 : 0;
+    }
+}
+cudaError_t launch_top_grid(const float2* bounds_cell, int ncx, int ncy, int ncz, uint8_t* top, int tx, int ty, int tz,
+                            int cells_per_top, cudaStream_t stream)
+{
+    size_t total = (size_t)tx * ty * tz;
+    k_top_grid<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, ncx, ncy, ncz, top, tx, ty, tz, cells_per_top);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// precomputed sun opacity (K.cu:483-553): per voxel, the Riemann sum of the (filtered) density toward the
+// sun with dt = 0.001 up to the box exit -- the same float sequence as the reference (t += dt, opacity +=
+// sample, final * dt).  Only voxels the path kernel can read are computed: the 9^3 apron block of every
+// non-empty brick (a scatter point always lies in a non-empty brick), stored per brick slot.
+// ---------------------------------------------------------------------------------------------------
+template <int VT>
+__global__ void __launch_bounds__(256) k_precompute_opacity(const __grid_constant__ Scene S, const uint32_t* __restrict__ slot_brick,
+                                                             uint32_t n_slots, float* __restrict__ out, float3 light_dir)
+{
+    const float  dt    = 0.001f;
+    const size_t total = (size_t)n_slots * 729;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        uint32_t s = (uint32_t)(idx / 729);
+        int      t = (int)(idx % 729);
+        uint32_t b = slot_brick[s];
+        int      bx = (int)(b % S.nbx), by = (int)((b / S.nbx) % S.nby), bz = (int)(b / ((uint32_t)S.nbx * S.nby));
+        int      lx = t % 9, ly = (t / 9) % 9, lz = t / 81;
+        int      i = clampi(bx * 8 - 1 + lx, 0, S.nx - 1), j = clampi(by * 8 - 1 + ly, 0, S.ny - 1), k = clampi(bz * 8 - 1 + lz, 0, S.nz - 1);
+        // normalized_coord + to_world (K.cu:164-171)
+        float3 start0 = f3((i + 0.5f) / S.nx, (j + 0.5f) / S.ny, (k + 0.5f) / S.nz);
+        float3 start  = start0 * (S.bmax - S.bmin) + S.bmin;
+        float  tn, tf;
+        box_slabs(S, start, light_dir, tn, tf);
+        bool hit = tf > tn && tf >= 1e-3f;
+        if (tn <= 0) tn = 0;
+        float opacity = 0.0f;
+        if (hit)
+        {
+            for (float tt = tn; tt < tf; tt += dt)
+            {
+                float3 pos = start + light_dir * tt;
+                opacity += fetch_density_parity<VT>(S, pos);
+            }
+            opacity *= dt;
+        }
+        out[(size_t)s * kOpBrickPad + t] = opacity;
+    }
+}
+cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick, uint32_t n_slots, float* opacity_bricks,
+                                      float3 light_dir, cudaStream_t stream)
+{
+    if (n_slots == 0) return cudaSuccess;
+    size_t       total = (size_t)n_slots * 729;
+    unsigned int g     = grid_for(total, 256, (size_t)148 * 64);
+    if (S.voxel_type == kF32)
+        k_precompute_opacity<kF32><<<g, 256, 0, stream>>>(S, slot_brick, n_slots, opacity_bricks, light_dir);
+    else if (S.voxel_type == kF16)
+        k_precompute_opacity<kF16><<<g, 256, 0, stream>>>(S, slot_brick, n_slots, opacity_bricks, light_dir);
+    else
+        k_precompute_opacity<kU8><<<g, 256, 0, stream>>>(S, slot_brick, n_slots, opacity_bricks, light_dir);
+    return cudaGetLastError();
+}
+
+// test helper: the opacity table as a dense [nz][ny][nx] array (0 where no brick stores the voxel)
+__global__ void __launch_bounds__(256) k_gather_opacity(const __grid_constant__ Scene S, float* __restrict__ dense_out)
+{
+    size_t total = (size_t)S.nx * S.ny * S.nz;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        int i = (int)(idx % S.nx), j = (int)((idx / S.nx) % S.ny), k = (int)(idx / ((size_t)S.nx * S.ny));
+        // voxel i is corner 0 of cell' i+1
+        uint32_t slot = brick_slot(S, i + 1, j + 1, k + 1);
+        float    v    = 0.0f;
+        if (slot != kEmptyBrick)
+        {
+            int lx = (i + 1) & 7, ly = (j + 1) & 7, lz = (k + 1) & 7;
+            v      = S.opacity[(size_t)slot * kOpBrickPad + (lz * 9 + ly) * 9 + lx];
+        }
+        dense_out[idx] = v;
+    }
+}
+cudaError_t launch_gather_opacity(const Scene& S, float* dense_out, cudaStream_t stream)
+{
+    size_t total = (size_t)S.nx * S.ny * S.nz;
+    k_gather_opacity<<<grid_for(total, 256), 256, 0, stream>>>(S, dense_out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// resolve (K.cu:2333-2362): dst = src * scale, or pow(src * scale, 1/gamma) with w = 1
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scale(float4* __restrict__ dst, const float4* __restrict__ src, int size, float scale)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= size) return;
+    float4 v = src[idx];
+    dst[idx] = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+}
+__global__ void __launch_bounds__(256) k_gamma(float4* __restrict__ dst, const float4* __restrict__ src, int size, float scale,
+                                                float gamma)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= size) return;
+    float4 v = src[idx];
+    dst[idx] = make_float4(powf(v.x * scale, gamma), powf(v.y * scale, gamma), powf(v.z * scale, gamma), 1.0f);
+}
+cudaError_t launch_resolve(float4* dst, const float4* src, int size, float scale, float gamma, cudaStream_t stream)
+{
+    if (size <= 0) return cudaSuccess;
+    int g = (size + 255) / 256;
+    if (gamma > 0.0f)
+        k_gamma<<<g, 256, 0, stream>>>(dst, src, size, scale, 1.0f / gamma);
+    else
+        k_scale<<<g, 256, 0, stream>>>(dst, src, size, scale);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// probes for tests
+// ---------------------------------------------------------------------------------------------------
+template <int VT>
+__global__ void k_fetch_density(const __grid_constant__ Scene S, const float3* __restrict__ pos, int n, int parity,
+                                float* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 p = pos[i];
+    if (parity)
+        out[i] = fetch_density_parity<VT>(S, p);
+    else
+    {
+        float3 q = (p - S.bmin) * S.l_inv;
+        out[i]   = fetch_density_fast<VT>(S, q.x * S.nx, q.y * S.ny, q.z * S.nz);
+    }
+}
+cudaError_t launch_fetch_density(const Scene& S, const float3* pos, int n, int parity, float* out, cudaStream_t stream)
+{
+    int g = (n + 127) / 128;
+    if (S.voxel_type == kF32)
+        k_fetch_density<kF32><<<g, 128, 0, stream>>>(S, pos, n, parity, out);
+    else if (S.voxel_type == kF16)
+        k_fetch_density<kF16><<<g, 128, 0, stream>>>(S, pos, n, parity, out);
+    else
+        k_fetch_density<kU8><<<g, 128, 0, stream>>>(S, pos, n, parity, out);
+    return cudaGetLastError();
+}
+
+__global__ void k_rng_sequence(uint32_t x, uint32_t y, uint32_t frame, int n, float* out_f, uint32_t* out_u)
+{
+    RefRng r;
+    r.init(x, y, frame);
+    for (int i = 0; i < n; i++)
+    {
+        uint32_t u = r.next_u32();
+        if (out_u) out_u[i] = u;
+        if (out_f) out_f[i] = u32_to_unit_float(u);
+    }
+}
+cudaError_t launch_rng_sequence(uint32_t x, uint32_t y, uint32_t frame, int n, float* out_f, uint32_t* out_u, cudaStream_t stream)
+{
+    k_rng_sequence<<<1, 1, 0, stream>>>(x, y, frame, n, out_f, out_u);
+    return cudaGetLastError();
+}
+__global__ void k_philox(uint32_t c0, uint32_t c1, uint32_t key, uint32_t* out2)
+{
+    uint32_t a, b;
+    philox2x32_10(c0, c1, key, a, b);
+    out2[0] = a;
+    out2[1] = b;
+}
+cudaError_t launch_philox(uint32_t c0, uint32_t c1, uint32_t key, uint32_t* out2, cudaStream_t stream)
+{
+    k_philox<<<1, 1, 0, stream>>>(c0, c1, key, out2);
+    return cudaGetLastError();
+}
+}  // namespace vp

@@ -1,0 +1,396 @@
+// volpath_common.cuh -- device-side building blocks shared by the volpath kernels (sm_100a).
+//
+// Reference citations: K.cu = src/volumeRender_kernel.cu, H.cpp = src/volumeRender.cpp of
+// RNG65536/CUDA-volpath.  Nothing here is copied from the reference; the functions restate what the
+// reference computes on our own data layout:
+//
+//   * density lives in HBM as a BRICKED OCTET STORE: the grid of trilinear cells (i,j,k),
+//     i in [-1, N-1], is cut into 8^3-cell bricks; an L2-resident brick table maps a brick to a slot
+//     in the octet pool or to EMPTY (all 8 corners of all its cells are zero); a slot holds, for
+//     each of its 512 cells, the cell's 8 corner voxels contiguously (clamped at the grid border, so
+//     clamp addressing costs nothing at fetch time).  A trilinear fetch is ONE table load and ONE
+//     32-byte (fp32) / 16-byte (fp16) / 8-byte (u8) load -- exactly one DRAM sector -- instead of
+//     eight scattered texel reads.  The 8x redundancy is paid in HBM capacity (180 GB on B200) and
+//     won back by skipping empty bricks.
+//   * the reference's per-voxel (max,min) bound texture (K.cu:392-412, H.cpp:1089-1267) is kept per
+//     voxel for the parity renderer and per 8^3-voxel cell for the fast renderer.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vp
+{
+constexpr int      kBrickLog2   = 3;
+constexpr int      kBrick       = 1 << kBrickLog2;           // cells per brick edge
+constexpr int      kBrickCells  = kBrick * kBrick * kBrick;  // 512
+constexpr int      kCellLog2    = 3;                          // bound cells: 8^3 voxels
+constexpr int      kOpBrick     = 9 * 9 * 9;                  // opacity brick: 9^3 voxels (with apron)
+constexpr int      kOpBrickPad  = 736;                        // padded to a multiple of 32 bytes
+constexpr uint32_t kEmptyBrick  = 0xFFFFFFFFu;
+constexpr float    kSearchRadius = 0.05f;                     // K.cu:151
+constexpr int      kMaxDepth     = 800;                       // K.cu:34
+
+enum VoxelType { kU8 = 0, kF16 = 1, kF32 = 2 };
+
+// Everything a render kernel reads, passed as one __grid_constant__ struct.
+struct Scene
+{
+    int    nx, ny, nz;       // voxels
+    int    nbx, nby, nbz;    // bricks (cells 0..N per axis, cell' = i + 1)
+    int    ncx, ncy, ncz;    // bound cells
+    int    voxel_type, linear, julia, have_opacity;
+    float3 bmin, bmax, l_inv;  // K.cu:155-159 (min, max, 1/(max-min))
+    const uint32_t* brick_table;
+    const void*     octets;
+    const float2*   bounds_voxel;  // [nz][ny][nx] (max,min)   -- parity
+    const float2*   bounds_cell;   // [ncz][ncy][ncx] (max,min) -- fast
+    const float*    opacity;       // per brick slot: 9^3 floats (+pad)
+    const float4*   env;           // [env_h][env_w]
+    int             env_w, env_h;
+    float3          sun_dir, sun_power, sun_power_original;  // K.cu:1254-1256
+    float           inv_view[12];                            // K.cu:626
+    // fast renderer: world -> voxel space (p * N) as one FMA per axis, and the top-level occupancy grid
+    float3          vs_scale, vs_off;
+    float           cam_z;           // (float)(-1.0f / tan(54.43f * 0.00872664626)) evaluated on the host (K.cu:1981-1985)
+    const uint8_t*  top;             // [tz][ty][tx], 1 = some medium within reach of the block
+    int             tx, ty, tz, top_shift;  // top cell = (8 << top_shift)... voxels per edge = 1 << top_shift
+};
+
+// ---- float3 helpers (operation order of src/cuda/helper_math.h) --------------------------------
+__device__ __forceinline__ float3 f3(float a, float b, float c) { return make_float3(a, b, c); }
+__device__ __forceinline__ float3 f3(float a) { return make_float3(a, a, a); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ float  dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b)
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize3(float3 v) { return v * rsqrtf(dot3(v, v)); }  // helper_math.h:1309
+__device__ __forceinline__ float  max_of(float3 v) { return fmaxf(fmaxf(v.x, v.y), v.z); }
+__device__ __forceinline__ float  min_of(float3 v) { return fminf(fminf(v.x, v.y), v.z); }
+__device__ __forceinline__ float3 fmin3(float3 a, float3 b) { return f3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+__device__ __forceinline__ float3 fmax3(float3 a, float3 b) { return f3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+
+// src/vecmath.h:9-16
+constexpr float kPi     = 3.1415926535897932384626422832795028841971f;
+constexpr float kTwoPi  = kPi * 2.0f;
+constexpr float kPi2    = kPi / 2.0f;
+constexpr float k1Pi    = 1.0f / kPi;
+constexpr float k1TwoPi = 1.0f / kTwoPi;
+
+// ---- RNG ---------------------------------------------------------------------------------------
+// Reference stream (src/sampler.h:3-46): Wang hash seeding of ((x<<16)|y, frame), xoroshiro64*,
+// float from the top 23 bits.  Integer work: bit-exact.
+__host__ __device__ __forceinline__ uint32_t wang_hash(uint32_t seed)
+{
+    seed = (seed ^ 61u) ^ (seed >> 16);
+    seed *= 9u;
+    seed = seed ^ (seed >> 4);
+    seed *= 0x27d4eb2du;
+    seed = seed ^ (seed >> 15);
+    return seed;
+}
+__device__ __forceinline__ float u32_to_unit_float(uint32_t r)  // sampler.h:24-28
+{
+    return __uint_as_float(0x3f800000u | (r >> 9)) - 1.0f;
+}
+struct RefRng
+{
+    uint32_t sx, sy;
+    __device__ __forceinline__ uint32_t next_u32()
+    {
+        uint32_t result = sx * 0x9e3779bbu;
+        sy ^= sx;
+        sx = __funnelshift_l(sx, sx, 26) ^ sy ^ (sy << 9);
+        sy = __funnelshift_l(sx, sx, 13);
+        return result;
+    }
+    __device__ __forceinline__ void init(uint32_t px, uint32_t py, uint32_t frame)
+    {
+        sx = wang_hash((px << 16) | py);
+        sy = wang_hash(frame);
+        next_u32();
+    }
+    __device__ __forceinline__ float next() { return u32_to_unit_float(next_u32()); }
+};
+
+// Philox2x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel Random Numbers: As Easy as 1, 2, 3", SC'11):
+// counter (c0, c1), key k; 10 rounds of {hi,lo = M*c0; (c0,c1) = (hi^k^c1, lo); k += W}.
+// The fast renderer uses counter = (draw index, frame), key = pixel: any (pixel, frame, draw) triple
+// is addressable without carried state, so a regenerated lane needs no RNG hand-over.
+__host__ __device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t k, uint32_t& o0, uint32_t& o1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++)
+    {
+        uint64_t p  = (uint64_t)0xD256D193u * c0;
+        uint32_t hi = (uint32_t)(p >> 32), lo = (uint32_t)p;
+        c0 = hi ^ k ^ c1;
+        c1 = lo;
+        k += 0x9E3779B9u;
+    }
+    o0 = c0;
+    o1 = c1;
+}
+
+// ---- octet store -------------------------------------------------------------------------------
+template <int VT> struct OctetBytes;
+template <> struct OctetBytes<kU8> { static constexpr int value = 8; };
+template <> struct OctetBytes<kF16> { static constexpr int value = 16; };
+template <> struct OctetBytes<kF32> { static constexpr int value = 32; };
+
+// the 8 corners of one cell as floats, v[dz*4 + dy*2 + dx]; u8 is returned UN-normalised (0..255)
+template <int VT>
+__device__ __forceinline__ void load_octet(const void* pool, size_t cell_index, float v[8])
+{
+    if (VT == kF32)
+    {
+        const float4* p = reinterpret_cast<const float4*>(pool) + cell_index * 2;
+        float4        a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    else if (VT == kF16)
+    {
+        uint4   a = __ldg(reinterpret_cast<const uint4*>(pool) + cell_index);
+        __half2 h0 = *reinterpret_cast<__half2*>(&a.x), h1 = *reinterpret_cast<__half2*>(&a.y);
+        __half2 h2 = *reinterpret_cast<__half2*>(&a.z), h3 = *reinterpret_cast<__half2*>(&a.w);
+        float2  f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3_ = __half22float2(h3);
+        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3_.x; v[7] = f3_.y;
+    }
+    else
+    {
+        uint2 a = __ldg(reinterpret_cast<const uint2*>(pool) + cell_index);
+        v[0] = (float)(a.x & 0xff); v[1] = (float)((a.x >> 8) & 0xff); v[2] = (float)((a.x >> 16) & 0xff); v[3] = (float)(a.x >> 24);
+        v[4] = (float)(a.y & 0xff); v[5] = (float)((a.y >> 8) & 0xff); v[6] = (float)((a.y >> 16) & 0xff); v[7] = (float)(a.y >> 24);
+    }
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
+
+// slot lookup for cell' = (cx, cy, cz), each in [0, N]
+__device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, int cz)
+{
+    int bx = cx >> kBrickLog2, by = cy >> kBrickLog2, bz = cz >> kBrickLog2;
+    return __ldg(S.brick_table + ((size_t)bz * S.nby + by) * S.nbx + bx);
+}
+__device__ __forceinline__ size_t cell_in_slot(uint32_t slot, int cx, int cy, int cz)
+{
+    return (size_t)slot * kBrickCells + (((cz & (kBrick - 1)) << (2 * kBrickLog2)) | ((cy & (kBrick - 1)) << kBrickLog2) | (cx & (kBrick - 1)));
+}
+
+// PARITY density fetch: restates the CUDA texture unit exactly as oracle/tex_emul.h does
+// (K.cu:173-178 sample_w: p = (pos-min)*l_inv; clamp addressing; point: floor(p*N); linear:
+// xB = p*N - 0.5, 1.8 fixed-point weights, (1-a)*p + a*q without contraction; u8 -> /255).
+template <int VT>
+__device__ __forceinline__ float fetch_density_parity(const Scene& S, float3 pos)
+{
+    float3 p = (pos - S.bmin) * S.l_inv;
+    float  x = __fmul_rn(p.x, (float)S.nx), y = __fmul_rn(p.y, (float)S.ny), z = __fmul_rn(p.z, (float)S.nz);
+    float  v[8];
+    if (!S.linear)
+    {
+        int      ix = clampi((int)floorf(x), 0, S.nx - 1) + 1, iy = clampi((int)floorf(y), 0, S.ny - 1) + 1,
+                 iz = clampi((int)floorf(z), 0, S.nz - 1) + 1;
+        uint32_t slot = brick_slot(S, ix, iy, iz);
+        if (slot == kEmptyBrick) return 0.0f;
+        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+        return VT == kU8 ? __fdiv_rn(v[0], 255.0f) : v[0];
+    }
+    float xb = __fsub_rn(x, 0.5f), yb = __fsub_rn(y, 0.5f), zb = __fsub_rn(z, 0.5f);
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    float a = __fsub_rn(xb, fx), b = __fsub_rn(yb, fy), g = __fsub_rn(zb, fz);
+    a = __fmul_rn(floorf(__fadd_rn(__fmul_rn(a, 256.0f), 0.5f)), 1.0f / 256.0f);
+    b = __fmul_rn(floorf(__fadd_rn(__fmul_rn(b, 256.0f), 0.5f)), 1.0f / 256.0f);
+    g = __fmul_rn(floorf(__fadd_rn(__fmul_rn(g, 256.0f), 0.5f)), 1.0f / 256.0f);
+    // cell' = floor(xB) + 1 clamped to [0, N]; the stored corners are already border-clamped
+    int ix = clampi((int)fx + 1, 0, S.nx), iy = clampi((int)fy + 1, 0, S.ny), iz = clampi((int)fz + 1, 0, S.nz);
+    uint32_t slot = brick_slot(S, ix, iy, iz);
+    if (slot == kEmptyBrick) return 0.0f;
+    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    if (VT == kU8)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __fdiv_rn(v[i], 255.0f);
+    }
+    float ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b), ig = __fsub_rn(1.0f, g);
+    float c00 = __fadd_rn(__fmul_rn(ia, v[0]), __fmul_rn(a, v[1]));
+    float c10 = __fadd_rn(__fmul_rn(ia, v[2]), __fmul_rn(a, v[3]));
+    float c01 = __fadd_rn(__fmul_rn(ia, v[4]), __fmul_rn(a, v[5]));
+    float c11 = __fadd_rn(__fmul_rn(ia, v[6]), __fmul_rn(a, v[7]));
+    float c0  = __fadd_rn(__fmul_rn(ib, c00), __fmul_rn(b, c10));
+    float c1  = __fadd_rn(__fmul_rn(ib, c01), __fmul_rn(b, c11));
+    return __fadd_rn(__fmul_rn(ig, c0), __fmul_rn(g, c1));
+}
+
+// FAST density fetch: same sample point and neighbours, full-precision weights, fused lerps.
+// `vs` = voxel-space position p*N (already scaled by the caller).
+template <int VT>
+__device__ __forceinline__ float fetch_density_fast(const Scene& S, float x, float y, float z)
+{
+    float v[8];
+    if (!S.linear)
+    {
+        int      ix = clampi(__float2int_rd(x), 0, S.nx - 1) + 1, iy = clampi(__float2int_rd(y), 0, S.ny - 1) + 1,
+                 iz = clampi(__float2int_rd(z), 0, S.nz - 1) + 1;
+        uint32_t slot = brick_slot(S, ix, iy, iz);
+        if (slot == kEmptyBrick) return 0.0f;
+        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+        return VT == kU8 ? v[0] * (1.0f / 255.0f) : v[0];
+    }
+    float xb = x - 0.5f, yb = y - 0.5f, zb = z - 0.5f;
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    float a = xb - fx, b = yb - fy, g = zb - fz;
+    int   ix = clampi((int)fx + 1, 0, S.nx), iy = clampi((int)fy + 1, 0, S.ny), iz = clampi((int)fz + 1, 0, S.nz);
+    uint32_t slot = brick_slot(S, ix, iy, iz);
+    if (slot == kEmptyBrick) return 0.0f;
+    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    float c00 = fmaf(a, v[1] - v[0], v[0]);
+    float c10 = fmaf(a, v[3] - v[2], v[2]);
+    float c01 = fmaf(a, v[5] - v[4], v[4]);
+    float c11 = fmaf(a, v[7] - v[6], v[6]);
+    float c0  = fmaf(b, c10 - c00, c00);
+    float c1  = fmaf(b, c11 - c01, c01);
+    float r   = fmaf(g, c1 - c0, c0);
+    return VT == kU8 ? r * (1.0f / 255.0f) : r;
+}
+
+// Procedural density of the reference's no-OpenVDB build (K.cu:84-140): quaternion Julia set,
+// q <- q^2 + c until |q|^2 >= 10 or 31 iterations; density = (iterations > 27).
+__device__ __forceinline__ float julia_density(float3 pos)
+{
+    const float radius = 1.4f;
+    float       qx = pos.x * radius, qy = pos.y * radius, qz = pos.z * radius, qw = 0.0f;
+    int         iter = 0;
+    float       d;
+    do
+    {
+        float r0 = qx * qx - (qy * qy + qz * qz + qw * qw);
+        float t  = qx * 2;
+        float ry = qy * t, rz = qz * t, rw = qw * t;
+        qx = r0 + -0.2f; qy = ry + 0.8f; qz = rz + 0.0f; qw = rw + 0.0f;
+        d  = qx * qx + qy * qy + qz * qz + qw * qw;
+    } while (d < 10.0f && iter++ < 30);
+    return (float)(iter > 27);  // iter > 30 * 0.9
+}
+
+// opacity table: trilinear (1.8 fixed-point weights, always linear: K.cu:541-542) from 9^3 apron bricks
+__device__ __forceinline__ float fetch_opacity(const Scene& S, float3 pos, bool parity)
+{
+    float3 p = (pos - S.bmin) * S.l_inv;
+    float  x = __fmul_rn(p.x, (float)S.nx), y = __fmul_rn(p.y, (float)S.ny), z = __fmul_rn(p.z, (float)S.nz);
+    float  xb = __fsub_rn(x, 0.5f), yb = __fsub_rn(y, 0.5f), zb = __fsub_rn(z, 0.5f);
+    float  fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    float  a = __fsub_rn(xb, fx), b = __fsub_rn(yb, fy), g = __fsub_rn(zb, fz);
+    if (parity)
+    {
+        a = __fmul_rn(floorf(__fadd_rn(__fmul_rn(a, 256.0f), 0.5f)), 1.0f / 256.0f);
+        b = __fmul_rn(floorf(__fadd_rn(__fmul_rn(b, 256.0f), 0.5f)), 1.0f / 256.0f);
+        g = __fmul_rn(floorf(__fadd_rn(__fmul_rn(g, 256.0f), 0.5f)), 1.0f / 256.0f);
+    }
+    int ix = clampi((int)fx + 1, 0, S.nx), iy = clampi((int)fy + 1, 0, S.ny), iz = clampi((int)fz + 1, 0, S.nz);
+    uint32_t slot = brick_slot(S, ix, iy, iz);
+    if (slot == kEmptyBrick) return 0.0f;  // only reachable where the density is zero around pos
+    const float* B  = S.opacity + (size_t)slot * kOpBrickPad;
+    int          lx = ix & (kBrick - 1), ly = iy & (kBrick - 1), lz = iz & (kBrick - 1);
+    const float* q  = B + (lz * 9 + ly) * 9 + lx;
+    float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 9), v3 = __ldg(q + 10);
+    float v4 = __ldg(q + 81), v5 = __ldg(q + 82), v6 = __ldg(q + 90), v7 = __ldg(q + 91);
+    float ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b), ig = __fsub_rn(1.0f, g);
+    float c00 = __fadd_rn(__fmul_rn(ia, v0), __fmul_rn(a, v1));
+    float c10 = __fadd_rn(__fmul_rn(ia, v2), __fmul_rn(a, v3));
+    float c01 = __fadd_rn(__fmul_rn(ia, v4), __fmul_rn(a, v5));
+    float c11 = __fadd_rn(__fmul_rn(ia, v6), __fmul_rn(a, v7));
+    float c0  = __fadd_rn(__fmul_rn(ib, c00), __fmul_rn(b, c10));
+    float c1  = __fadd_rn(__fmul_rn(ib, c01), __fmul_rn(b, c11));
+    return __fadd_rn(__fmul_rn(ig, c0), __fmul_rn(g, c1));
+}
+
+// ---- environment / sun (K.cu:882-895, 956-973, 1258-1267) -----------------------------------------
+__device__ __forceinline__ float3 eval_envmap(const Scene& S, float3 dir)
+{
+    float phi   = acosf(dir.y);
+    float theta = atanf(dir.z / dir.x) + kPi2;
+    if (dir.x < 0) theta += kPi;
+    float u = theta * k1TwoPi;
+    float v = phi * k1Pi;
+    // point filter, normalized coordinates, clamp (legacy texture reference defaults, K.cu:1099-1100)
+    int    i = clampi((int)floorf(__fmul_rn(u, (float)S.env_w)), 0, S.env_w - 1);
+    int    j = clampi((int)floorf(__fmul_rn(v, (float)S.env_h)), 0, S.env_h - 1);
+    float4 c = __ldg(S.env + (size_t)j * S.env_w + i);
+    return f3(c.x, c.y, c.z);
+}
+__device__ __forceinline__ float3 background(const Scene& S, float3 dir, int depth)
+{
+    if (depth == 0 && (dot3(dir, S.sun_dir) > 94.0f / sqrtf(94.0f * 94.0f + 0.45f * 0.45f))) return S.sun_power_original;
+    return eval_envmap(S, dir);
+}
+
+// Henyey-Greenstein (K.cu:575-619); sampling clamps cos(theta) to [0,1] like the reference (Q3)
+__device__ __forceinline__ float hg_evaluate(float g, float cos_theta)
+{
+    return (1.0f - g * g) / (4.0f * kPi * powf(1.0f + g * g - 2 * g * cos_theta, 1.5f));
+}
+__device__ __forceinline__ float3 hg_sample_local(float g, float rnd0, float rnd1)
+{
+    float cos_theta;
+    if (fabsf(g) > 1e-6f)
+    {
+        float s   = 2.0f * rnd0 - 1.0f;
+        float f   = (1.0f - g * g) / (1.0f + g * s);
+        cos_theta = (0.5f / g) * (1.0f + g * g - f * f);
+        cos_theta = fmaxf(0.0f, fminf(1.0f, cos_theta));
+    }
+    else
+    {
+        cos_theta = 2.0f * rnd0 - 1.0f;
+    }
+    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    float phi       = 2.0f * kPi * rnd1;
+    return f3(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta);
+}
+// Frame (K.cu:557-573): orthonormal basis around n
+__device__ __forceinline__ void make_frame(float3 n, float3& t, float3& b)
+{
+    float3 a = (double)fabsf(n.x) > 0.1 ? f3(0, 1, 0) : f3(1, 0, 0);
+    t        = normalize3(cross3(a, n));
+    b        = cross3(n, t);
+}
+
+// slab test shared by intersectBox / intersect_box / intersectSuperVolume (K.cu:453-481, 654-680, 1626-1661)
+__device__ __forceinline__ void box_slabs(const Scene& S, float3 o, float3 d, float& largest_tmin, float& smallest_tmax)
+{
+    float3 invR = f3(1.0f) / d;
+    float3 tbot = invR * (S.bmin - o);
+    float3 ttop = invR * (S.bmax - o);
+    largest_tmin  = max_of(fmin3(ttop, tbot));
+    smallest_tmax = min_of(fmax3(ttop, tbot));
+}
+
+// camera ray of pixel (x, y) (K.cu:1977-1987).  tan() is evaluated in double like the reference (Q7).
+__device__ __forceinline__ void camera_ray(const Scene& S, uint32_t x, uint32_t y, uint32_t W, uint32_t H, float3& o, float3& d)
+{
+    float u    = (x * 2.0f - W) / W;
+    float v    = (y * 2.0f - H) / W;
+    float fovx = 54.43;
+    const float* M = S.inv_view;
+    o = f3(M[3], M[7], M[11]);
+    float3 dc = f3(u, v, (float)(-1.0f / tan(fovx * 0.00872664626)));
+    d = normalize3(f3(dot3(dc, f3(M[0], M[1], M[2])), dot3(dc, f3(M[4], M[5], M[6])), dot3(dc, f3(M[8], M[9], M[10]))));
+}
+// same ray with the per-launch constant hoisted to the host (fast renderer)
+__device__ __forceinline__ void camera_ray_fast(const Scene& S, uint32_t x, uint32_t y, uint32_t W, uint32_t H, float3& o, float3& d)
+{
+    float u = (x * 2.0f - W) / W;
+    float v = (y * 2.0f - H) / W;
+    const float* M = S.inv_view;
+    o = f3(M[3], M[7], M[11]);
+    float3 dc = f3(u, v, S.cam_z);
+    d = normalize3(f3(dot3(dc, f3(M[0], M[1], M[2])), dot3(dc, f3(M[4], M[5], M[6])), dot3(dc, f3(M[8], M[9], M[10]))));
+}
+}  // namespace vp

@@ -1,0 +1,47 @@
+// volpath_kernels.h -- host-callable launchers of the volpath CUDA kernels (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/volpath.h"
+
+namespace vp
+{
+struct Scene;
+
+// --- rendering (volpath_render_parity.cu, volpath_render_fast.cu, volpath_render_wave.cu) --------------
+cudaError_t launch_render_parity(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride,
+                                 const vp_param& P, cudaStream_t stream);
+// d_stats: 8 device counters {track fetches, shadow fetches, segments, opacity fetches, env evaluations,
+// scatters, -, -} or nullptr (the uninstrumented kernel)
+cudaError_t launch_render_fast(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride,
+                               const vp_param& P, unsigned long long* d_stats, cudaStream_t stream);
+cudaError_t launch_resolve(float4* dst, const float4* src, int size, float scale, float gamma, cudaStream_t stream);
+
+// --- scene build (volpath_build.cu) ---------------------------------------------------------------------
+cudaError_t launch_fbm_cloud(float* d_dense, int nx, int ny, int nz, uint32_t seed, cudaStream_t stream);
+cudaError_t launch_u8_to_f32(const uint8_t* src, float* dst, size_t n, cudaStream_t stream);
+// one axis of the separable clamped-window (max,min): in [n2][n1][n0] -> out with the swept axis reduced by
+// `cell` (out index c covers inputs [c*cell - D, c*cell + cell - 1 + D])
+cudaError_t launch_bounds_axis_f32(const float* in, float2* out, int n0, int n1, int n2, int axis, int D, int cell,
+                                   cudaStream_t stream);
+cudaError_t launch_bounds_axis(const float2* in, float2* out, int n0, int n1, int n2, int axis, int D, int cell,
+                               cudaStream_t stream);
+cudaError_t launch_classify_bricks(const float* dense, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* flags,
+                                   cudaStream_t stream);
+cudaError_t launch_make_table(const uint32_t* flags, const uint32_t* scan, size_t nb, int nbx, int nby, uint32_t* table,
+                              uint32_t* slot_brick, cudaStream_t stream);
+cudaError_t launch_fill_octets(const float* dense, int nx, int ny, int nz, int nbx, int nby, const uint32_t* slot_brick,
+                               uint32_t n_slots, void* pool, int voxel_type, cudaStream_t stream);
+cudaError_t launch_top_grid(const float2* bounds_cell, int ncx, int ncy, int ncz, uint8_t* top, int tx, int ty, int tz,
+                            int cells_per_top, cudaStream_t stream);
+cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick, uint32_t n_slots, float* opacity_bricks,
+                                      float3 light_dir, cudaStream_t stream);
+cudaError_t launch_gather_opacity(const Scene& S, float* dense_out, cudaStream_t stream);
+
+// --- probes for tests -------------------------------------------------------------------------------------
+cudaError_t launch_fetch_density(const Scene& S, const float3* pos, int n, int parity, float* out, cudaStream_t stream);
+cudaError_t launch_rng_sequence(uint32_t x, uint32_t y, uint32_t frame, int n, float* out_f, uint32_t* out_u,
+                                cudaStream_t stream);
+cudaError_t launch_philox(uint32_t c0, uint32_t c1, uint32_t key, uint32_t* out2, cudaStream_t stream);
+}  // namespace vp

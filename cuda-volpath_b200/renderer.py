@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's render interface for the hot path.
+
+`Renderer` keeps the call names and argument meaning of the reference's `extern "C"` surface
+(src/volumeRender.cpp:117-128, 347-356: init_cuda, set_texture_filter_mode, init_envmap, set_sun,
+copy_inv_view_matrix, precompute_opacity, render_kernel, scale, gamma_correct) on top of one vp_context.
+Device memory for the float4 accumulator is a torch CUDA tensor (plumbing only); every computation is a
+kernel of libvolpath_b200.so reached through the C ABI."""
+import ctypes
+
+import numpy as np
+
+from . import lib as _l
+from .param import Param
+
+
+def _fp(a):
+    return a.ctypes.data_as(_l.c_fp)
+
+
+class Renderer:
+    def __init__(self, device=0):
+        self.L = _l.load()
+        self.device = device
+        h = _l.c_vp()
+        _l.check(self.L.vp_create(device, ctypes.byref(h)))
+        self.h = h
+        self.dims = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene (reference names) ---------------------------------------------------------------------
+    def init_cuda(self, volume, quantized, box=None, store=None, bounds=_l.BOUNDS_VOXEL | _l.BOUNDS_CELL):
+        """init_cuda (K.cu:354): dense host volume [nz, ny, nx] (x fastest), uint8 if quantized else float32."""
+        vol = np.ascontiguousarray(volume)
+        if vol.dtype != (np.uint8 if quantized else np.float32):
+            raise TypeError("quantized volumes are uint8, others float32")
+        nz, ny, nx = vol.shape
+        src = _l.VOXEL_U8 if quantized else _l.VOXEL_F32
+        store = src if store is None else store
+        lo = hi = None
+        if box is not None:
+            self._lo, self._hi = np.asarray(box[0], np.float32), np.asarray(box[1], np.float32)
+            lo, hi = _fp(self._lo), _fp(self._hi)
+        _l.check(self.L.vp_upload_volume(self.h, vol.ctypes.data, nx, ny, nz, src, store, _l.MEM_HOST, lo, hi, bounds))
+        self.dims = (nx, ny, nz)
+
+    def generate_cloud(self, nx, ny, nz, seed=0, store=_l.VOXEL_F32, bounds=_l.BOUNDS_CELL, keep_dense=False, box=None):
+        lo = hi = None
+        if box is not None:
+            self._lo, self._hi = np.asarray(box[0], np.float32), np.asarray(box[1], np.float32)
+            lo, hi = _fp(self._lo), _fp(self._hi)
+        _l.check(self.L.vp_generate_cloud(self.h, nx, ny, nz, seed, store, lo, hi, bounds, int(keep_dense)))
+        self.dims = (nx, ny, nz)
+
+    def set_julia(self):
+        _l.check(self.L.vp_set_julia(self.h))
+        self.dims = None
+
+    def set_texture_filter_mode(self, linear):
+        _l.check(self.L.vp_set_filter(self.h, int(bool(linear))))
+
+    def init_envmap(self, env):
+        env = np.ascontiguousarray(env, np.float32)
+        assert env.ndim == 3 and env.shape[2] == 4
+        _l.check(self.L.vp_set_envmap(self.h, _fp(env), env.shape[1], env.shape[0]))
+
+    def set_sun(self, sun_dir, sun_power):
+        d, p = np.ascontiguousarray(sun_dir, np.float32), np.ascontiguousarray(sun_power, np.float32)
+        _l.check(self.L.vp_set_sun(self.h, _fp(d), _fp(p)))
+
+    def copy_inv_view_matrix(self, m12):
+        m = np.ascontiguousarray(m12, np.float32)
+        assert m.size == 12
+        _l.check(self.L.vp_set_inv_view(self.h, _fp(m)))
+
+    def precompute_opacity(self, sun_dir):
+        d = np.ascontiguousarray(sun_dir, np.float32)
+        _l.check(self.L.vp_precompute_opacity(self.h, _fp(d)))
+
+    def free_cuda_buffers(self):
+        _l.check(self.L.vp_free_volume(self.h))
+
+    # ---- render ----------------------------------------------------------------------------------------
+    def render_kernel(self, d_sum_ptr, spp, param, mode=_l.MODE_PARITY, n_frames=1, frame_stride=1, stream=None):
+        """render_kernel (K.cu:2364): add frame(s) into the device float4[W*H] sum at d_sum_ptr."""
+        _l.check(self.L.vp_render(self.h, d_sum_ptr, spp, n_frames, frame_stride, ctypes.byref(param), mode, stream))
+
+    def render(self, param, first_frame, n_frames, mode=_l.MODE_FAST, frame_stride=1, accum=None):
+        """Host-buffer form: returns the float32 [H, W, 4] sum after adding the frames."""
+        if accum is None:
+            accum = np.zeros((param.height, param.width, 4), np.float32)
+        assert accum.dtype == np.float32 and accum.flags["C_CONTIGUOUS"]
+        _l.check(self.L.vp_render_to_host(self.h, accum.ctypes.data, first_frame, n_frames, frame_stride,
+                                          ctypes.byref(param), mode))
+        return accum
+
+    def scale(self, dst_ptr, src_ptr, size, scale, stream=None):
+        _l.check(self.L.vp_resolve(self.h, dst_ptr, src_ptr, size, scale, 0.0, stream))
+
+    def gamma_correct(self, dst_ptr, src_ptr, size, scale, gamma, stream=None):
+        _l.check(self.L.vp_resolve(self.h, dst_ptr, src_ptr, size, scale, gamma, stream))
+
+    def sync(self):
+        _l.check(self.L.vp_sync(self.h))
+
+    # ---- introspection -----------------------------------------------------------------------------------
+    def bounds_voxel(self):
+        nx, ny, nz = self.dims
+        out = np.empty((nz, ny, nx, 2), np.float32)
+        _l.check(self.L.vp_get_bounds_voxel(self.h, _fp(out)))
+        return out
+
+    def bounds_cell(self):
+        d = (ctypes.c_int * 3)()
+        _l.check(self.L.vp_get_bounds_cell(self.h, None, d))
+        out = np.empty((d[2], d[1], d[0], 2), np.float32)
+        _l.check(self.L.vp_get_bounds_cell(self.h, _fp(out), d))
+        return out
+
+    def opacity(self):
+        nx, ny, nz = self.dims
+        out = np.empty((nz, ny, nx), np.float32)
+        _l.check(self.L.vp_get_opacity(self.h, _fp(out)))
+        return out
+
+    def fetch_density(self, pos, parity=True):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        out = np.empty(len(pos), np.float32)
+        _l.check(self.L.vp_fetch_density(self.h, _fp(pos), len(pos), int(parity), _fp(out)))
+        return out
+
+    def dense_volume(self):
+        """The device fp32 dense copy kept by generate_cloud(keep_dense=True), as a host array."""
+        nx, ny, nz = self.dims
+        p = self.L.vp_dense_volume(self.h)
+        if not p:
+            raise _l.VolpathError("no dense copy kept")
+        out = np.empty((nz, ny, nx), np.float32)
+        assert self.L.vp_dev_to_host(out.ctypes.data, p, out.nbytes) == 0
+        return out
+
+    def dense_volume_ptr(self):
+        return self.L.vp_dense_volume(self.h)
+
+    def volume_stats(self):
+        s = (ctypes.c_ulonglong * 8)()
+        _l.check(self.L.vp_volume_stats(self.h, s))
+        keys = ["bricks", "nonempty_bricks", "octet_bytes", "bound_radius_voxels", "bounds_cell_bytes",
+                "bounds_voxel_bytes", "opacity_bytes", "table_bytes"]
+        return dict(zip(keys, [int(v) for v in s]))
+
+    def rng_sequence(self, x, y, frame, n):
+        f = np.empty(n, np.float32)
+        u = np.empty(n, np.uint32)
+        _l.check(self.L.vp_rng_sequence(self.h, x, y, frame, n, _fp(f), u.ctypes.data_as(ctypes.POINTER(ctypes.c_uint))))
+        return f, u
+
+    def philox2x32(self, c0, c1, key):
+        o = (ctypes.c_uint * 2)()
+        _l.check(self.L.vp_philox2x32(self.h, c0, c1, key, o))
+        return int(o[0]), int(o[1])
+
+    def set_stats(self, on):
+        _l.check(self.L.vp_set_stats(self.h, int(on)))
+
+    def counters(self, reset=True):
+        s = (ctypes.c_ulonglong * 8)()
+        _l.check(self.L.vp_render_counters(self.h, s, int(reset)))
+        keys = ["track_fetches", "shadow_fetches", "segments", "opacity_fetches", "env_evals", "scatters"]
+        return dict(zip(keys, [int(v) for v in s][:6]))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float()
+        _l.check(self.L.vp_last_kernel_ms(self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        n = ctypes.c_ulonglong()
+        _l.check(self.L.vp_launch_count(self.h, ctypes.byref(n)))
+        return int(n.value)

@@ -1,0 +1,163 @@
+/* include/volpath.h -- C ABI of libvolpath_b200.so, the B200-native replacement of CUDA-volpath's
+ * render hot path.
+ *
+ * Two layers, both plain C (pointers, ints, floats; no torch / C++ types):
+ *
+ *  (1) reference-named shims: the 14 `extern "C"` entry points the reference's host code binds
+ *      (declared in src/volumeRender.cpp:117-128, 347-356; defined in src/volumeRender_kernel.cu),
+ *      same names, same argument meaning, same ABI.  A maintainer links this library instead of
+ *      compiling volumeRender_kernel.cu and nothing above the boundary changes.
+ *      They operate on one implicit default context on the current CUDA device, like the reference's
+ *      file-scope statics, but report failures through vp_last_error() instead of exit(1).
+ *
+ *  (2) the handle-based core the shims are built on (vp_*): one context per GPU, explicit stream,
+ *      int status returns (0 = ok, otherwise a cudaError_t value or a VP_ERR_* code).
+ *
+ * Layout conventions are the reference's: volumes are dense, x fastest (index i + j*nx + k*nx*ny,
+ * vdbloader/load_vdb.cpp:47-50), the accumulator is a device float4[W*H] SUM owned by the caller
+ * (CudaFrameBuffer, src/volumeRender.cpp:358-389), .w accumulates the scatter count, frame index
+ * `spp` is the RNG stream id (src/sampler.h:35-43).
+ */
+#ifndef VOLPATH_B200_H
+#define VOLPATH_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
+
+/* ---- plain-C mirrors of the CUDA vector types that cross the reference boundary ------------- */
+typedef struct vp_float3 { float x, y, z; } vp_float3;
+typedef struct vp_float4 { float x, y, z, w; } vp_float4;              /* 16-byte aligned in CUDA; device data */
+typedef struct vp_dim3 { unsigned int x, y, z; } vp_dim3;              /* = dim3 */
+typedef struct vp_extent { size_t width, height, depth; } vp_extent;  /* = cudaExtent */
+
+/* src/param.h:4-12 -- 44-byte POD, passed by value to the reference's kernels */
+typedef struct vp_param {
+    unsigned int width, height;
+    float        density, brightness;
+    vp_float3    albedo;
+    float        g;
+    vp_float3    sigma_t;
+} vp_param;
+
+typedef struct vp_context vp_context;
+typedef void*             vp_stream; /* cudaStream_t */
+
+enum { VP_OK = 0, VP_ERR_INVALID = 10001, VP_ERR_NO_VOLUME = 10002, VP_ERR_NO_DEVICE = 10003, VP_ERR_UNSUPPORTED = 10004 };
+
+/* voxel types: what the caller hands in (src) and what is stored in HBM (store) */
+enum { VP_VOXEL_U8 = 0, VP_VOXEL_F16 = 1, VP_VOXEL_F32 = 2 };
+enum { VP_MEM_HOST = 0, VP_MEM_DEVICE = 1 };
+
+/* local-bound ("majorant") grids built at upload time
+ *   VP_BOUNDS_VOXEL : per-voxel (max,min) over the clamped +-D voxel cube, D = ceil(0.05/(2/nx)) --
+ *                     bit-identical to the reference's compute_volume_value_bound_
+ *                     (src/volumeRender.cpp:1089-1267); needed by the parity renderer.
+ *   VP_BOUNDS_CELL  : per 8^3-voxel cell, (max,min) over cell +-D voxels (= max/min of the per-voxel
+ *                     bounds of the cell's voxels; conservative superset) -- used by the fast renderer.
+ * The flags can be or-ed. */
+enum { VP_BOUNDS_VOXEL = 1, VP_BOUNDS_CELL = 2 };
+
+/* render modes of vp_render
+ *   VP_MODE_PARITY : one thread per pixel, reference RNG (Wang hash + xoroshiro64*), reference draw
+ *                    order and segmenting; observationally identical to render_kernel.
+ *   VP_MODE_FAST   : tile-owning CTAs with per-lane path regeneration, Philox2x32-10 counter RNG, analytic
+ *                    skip of the empty-space march; same estimator in distribution. */
+enum { VP_MODE_PARITY = 0, VP_MODE_FAST = 1 };
+
+/* ---- (2) handle-based core -------------------------------------------------------------------- */
+const char* vp_last_error(void);                 /* message of the last failing call on this thread */
+const char* vp_version(void);
+int vp_create(int device, vp_context** out);     /* one context per GPU */
+int vp_destroy(vp_context* ctx);
+
+/* replaces init_cuda (K.cu:354-420): dense volume in, bricked "octet" store + bound grids out.
+ * boxmin/boxmax may be NULL -> +-(1, ny/nx, nz/nx) like the reference (K.cu:373-378). */
+int vp_upload_volume(vp_context* ctx, const void* volume, int nx, int ny, int nz, int src_voxel, int store_voxel,
+                     int memspace, const float* boxmin3, const float* boxmax3, int bounds_flags);
+/* synthetic fBm cloud generated on the device, bit-identical to
+ * oracle vo_fbm_cloud_f32; the dense fp32 copy is kept until vp_release_dense() when keep_dense != 0 */
+int vp_generate_cloud(vp_context* ctx, int nx, int ny, int nz, unsigned int seed, int store_voxel,
+                      const float* boxmin3, const float* boxmax3, int bounds_flags, int keep_dense);
+const void* vp_dense_volume(vp_context* ctx);    /* device fp32 dense copy, or NULL */
+int vp_release_dense(vp_context* ctx);
+/* config C1: the reference's no-OpenVDB build -- procedural Julia set, box [-1,1]^3, bounds (1,0) */
+int vp_set_julia(vp_context* ctx);
+int vp_set_filter(vp_context* ctx, int linear);                                   /* set_texture_filter_mode */
+int vp_set_envmap(vp_context* ctx, const float* rgba, int width, int height);     /* init_envmap, host ptr */
+int vp_set_sun(vp_context* ctx, const float* dir3, const float* power3);          /* set_sun */
+int vp_set_inv_view(vp_context* ctx, const float* m12);                           /* copy_inv_view_matrix */
+int vp_precompute_opacity(vp_context* ctx, const float* light_dir3);              /* precompute_opacity */
+int vp_free_volume(vp_context* ctx);                                              /* free_cuda_buffers */
+
+/* replaces render_kernel + the host frame loop: frames first_frame, first_frame+frame_stride, ...
+ * (n_frames of them) are added into d_sum.  n_frames = 1, stride 1, VP_MODE_PARITY is
+ * observationally identical to one render_kernel launch.  Asynchronous on `stream`. */
+int vp_render(vp_context* ctx, void* d_sum_float4, int first_frame, int n_frames, int frame_stride,
+              const vp_param* p, int mode, vp_stream stream);
+/* __scale / __gamma_correct (K.cu:2333-2362); gamma <= 0 -> plain scale */
+int vp_resolve(vp_context* ctx, void* d_dst_float4, const void* d_src_float4, int size, float scale, float gamma,
+               vp_stream stream);
+/* the host-buffer form of the same call (what the reference's capture() does around its kernel,
+ * src/volumeRender.cpp:585-610): h_sum is a HOST float4[W*H] sum; it is copied to the device, frames are
+ * added, and the result is copied back.  Synchronous. */
+int vp_render_to_host(vp_context* ctx, void* h_sum_float4, int first_frame, int n_frames, int frame_stride,
+                      const vp_param* p, int mode);
+int vp_sync(vp_context* ctx);
+
+/* introspection for tests / benchmarks */
+int vp_get_bounds_voxel(vp_context* ctx, float* h_out_maxmin);   /* [nz][ny][nx][2], (max,min) */
+int vp_get_bounds_cell(vp_context* ctx, float* h_out_maxmin, int* dims3); /* [cz][cy][cx][2] */
+int vp_get_opacity(vp_context* ctx, float* h_out);               /* [nz][ny][nx], 0 where not stored */
+int vp_fetch_density(vp_context* ctx, const float* h_pos3, int n, int parity_filter, float* h_out); /* world pos */
+int vp_volume_stats(vp_context* ctx, unsigned long long* out8);  /* bricks, nonempty bricks, bytes ... */
+int vp_rng_sequence(vp_context* ctx, unsigned int x, unsigned int y, unsigned int frame, int n, float* h_out_f,
+                    unsigned int* h_out_u);                      /* reference RNG stream, from the device */
+int vp_philox2x32(vp_context* ctx, unsigned int c0, unsigned int c1, unsigned int key, unsigned int* h_out2);
+int vp_set_stats(vp_context* ctx, int enable);                   /* fast mode: run the counting kernel variant */
+int vp_render_counters(vp_context* ctx, unsigned long long* out8, int reset); /* {track fetches, shadow fetches,
+                                                                    segments, opacity fetches, env evals, scatters} */
+int vp_last_kernel_ms(vp_context* ctx, float* ms);               /* CUDA-event time of the last vp_render */
+int vp_launch_count(vp_context* ctx, unsigned long long* n);     /* kernels launched by this context */
+
+/* plain device-memory helpers for C / ctypes callers without a CUDA runtime of their own */
+void* vp_dev_alloc(size_t bytes);                                /* zero-filled */
+int vp_dev_free(void* p);
+int vp_dev_zero(void* p, size_t bytes);
+int vp_dev_to_host(void* h, const void* d, size_t bytes);
+int vp_host_to_dev(void* d, const void* h, size_t bytes);
+
+/* ---- (1) reference-named shims (signatures: see the file:line next to each) ------------------- */
+void init_cuda(void* h_volume, vp_extent volumeSize, bool quantized, const vp_float3* boxmin,
+               const vp_float3* boxmax);                                 /* K.cu:354 */
+void set_texture_filter_mode(bool bLinearFilter);                 /* K.cu:422 */
+void free_cuda_buffers(void);                                             /* K.cu:441 */
+void precompute_opacity(const float* light_dir);                          /* K.cu:526 */
+void init_envmap(const vp_float4* HDRmap, int width, int height);         /* K.cu:1072 */
+void free_envmap(void);                                                   /* K.cu:1231 */
+void set_sun(float* sun_dir, float* sun_power);                           /* K.cu:1269 */
+void copy_inv_view_matrix(float* invViewMatrix, size_t sizeofMatrix);     /* K.cu:2320 */
+void copy_inv_model_matrix(float* invModelMatrix, size_t sizeofMatrix);   /* K.cu:2325 (USE_MODEL_TRANSFORM 0: stored, unused) */
+void init_rng(vp_dim3 gridSize, vp_dim3 blockSize, int width, int height);/* K.cu:2330 (empty in the reference) */
+void free_rng(void);                                                      /* K.cu:2331 */
+void scale(vp_float4* dst, vp_float4* src, int size, float scale);        /* K.cu:2343, device pointers */
+void gamma_correct(vp_float4* dst, vp_float4* src, int size, float scale, float gamma); /* K.cu:2359 */
+/* K.cu:2364: `const Param& p` in the reference; a C++ reference is a pointer at the ABI level */
+void render_kernel(vp_dim3 gridSize, vp_dim3 blockSize, vp_float4* d_output, int spp, const vp_param* p);
+/* which renderer the render_kernel shim uses (default VP_MODE_PARITY: drop-in identical) */
+void vp_shim_set_mode(int mode);
+vp_context* vp_shim_context(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLPATH_B200_H */

@@ -840,6 +840,14 @@ int vo_get_opacity(void* h, float* out)
     return 0;
 }
 
+// raw filtered density at world positions (CudaTexture::sample_w, K.cu:173-178) -- fetch-level tests
+int vo_sample_density(void* h, const float* pos3, int n, float* out)
+{
+    const Ctx& c = *(Ctx*)h;
+    for (int i = 0; i < n; i++) out[i] = sample_density_raw(c, v3(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2]));
+    return 0;
+}
+
 // render_kernel x n_frames (K.cu:2364-2370 + the host loop H.cpp:627-641): sum[x + y*W] += sample
 // stats8 (optional): totals of {track fetches, shadow fetches, segments, opacity fetches, env
 // evaluations, scatters} -- the L, S, O, E of SURVEY.md 8d.

@@ -317,69 +317,41 @@ def main():
                        "volume": stats, "setup_s": round(t_setup, 2)},
             "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
 
+    r.close()
+    del acc
+    torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
-        a2 = argparse.Namespace(**vars(args))
-        a2.steps, a2.warmup = 2, 1
-        _, _, cb = host_reference_run(a2, desc)
-        line["cpu_baseline"] = cb
+        j = run_tool([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                      "--steps", "2", "--warmup", "1"], 240)
+        line["cpu_baseline"] = j.get("cpu_baseline", j)
     if world == 1 and not args.no_ref_cuda and dims is not None:
-        line["ref_cuda"] = ref_cuda_compare(vp, r, P, env, sun_dir, sun_power, view, fps)
+        line["ref_cuda"] = ref_cuda_compare(local, fps)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def ref_cuda_compare(vp, r, P, env, sun_dir, sun_power, view, fps):
-    """The reference's own CUDA kernel rebuilt for sm_100 on this GPU, beside ours on the SAME scene.  The reference
-    layout needs 12 B/voxel of cudaArrays plus a CPU bound sweep (int-indexed, < 2^31 voxels), so the shared scene is
-    the C2 cloud family at 1/4 dims (497x338x612), same camera / Param / image size."""
-    import numpy as np
-    import torch
+def run_tool(cmd, timeout):
+    """Run a measurement leg in its own process (the reference libraries export the same symbol names as ours) and
+    return its one JSON line, or a reason."""
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        for ln in reversed(p.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": "rc %d: %s" % (p.returncode, (p.stderr or "").strip()[-300:])}
+    except Exception as e:  # timeout, missing file
+        return {"unavailable": repr(e)[:300]}
 
-    from oraclelib import RefCuda, have_ref
 
-    if not have_ref("libvolpath_ref_cuda.so"):
+def ref_cuda_compare(device, fps):
+    """The reference's own CUDA kernel rebuilt for sm_100, beside ours on the same scene and GPU
+    (tools/compare_ref_cuda.py, C2 cloud family at 1/4 dims -- what the reference's layout can hold)."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libvolpath_ref_cuda.so")):
         return {"unavailable": "oracle/_ref/libvolpath_ref_cuda.so not built"}
-    nx, ny, nz = WORKLOADS["c2q"][0]
-    r2 = vp.Renderer(r.device)
-    r2.generate_cloud(nx, ny, nz, seed=CLOUD_SEED, store=vp.VOXEL_F32, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL, keep_dense=True)
-    r2.set_texture_filter_mode(True)
-    r2.init_envmap(env)
-    r2.set_sun(sun_dir, sun_power)
-    r2.copy_inv_view_matrix(view)
-    r2.precompute_opacity(sun_dir)
-    # hand the reference our device volume and the (bit-identical) bound volume: its own CPU sweep would take minutes
-    ref = RefCuda()
-    bv = torch.empty(nz, ny, nx, 2, device="cuda")
-    import ctypes as C
-    vp.lib.check(0)
-    b_host = r2.bounds_voxel()
-    bv.copy_(torch.from_numpy(b_host))
-    rc = ref.L.ref_init_volume_device(r2.dense_volume_ptr(), bv.data_ptr(), nx, ny, nz, 0, None, None, 1)
-    assert rc == 0
-    ref.dims, ref.quantized = (nx, ny, nz), False
-    ref.set_envmap(env)
-    ref.set_sun(sun_dir, sun_power)
-    ref.set_inv_view(view)
-    ref.precompute_opacity(sun_dir)
-    acc = torch.zeros(P.height, P.width, 4, device="cuda")
-    ref.L.ref_render_timed(acc.data_ptr(), 0, 12, C.addressof(P))
-    ms_ref = ref.L.ref_render_timed(acc.data_ptr(), 12, fps, C.addressof(P))
-    acc2 = torch.zeros_like(acc)
-    stream = torch.cuda.current_stream().cuda_stream
-    r2.render_kernel(acc2.data_ptr(), 0, P, mode=vp.MODE_FAST, n_frames=12, stream=stream)
-    r2.render_kernel(acc2.data_ptr(), 12, P, mode=vp.MODE_FAST, n_frames=fps, stream=stream)
-    ms_ours = r2.last_kernel_ms()
-    n = P.width * P.height * fps
-    a, b = acc.cpu().numpy(), acc2.cpu().numpy()
-    out = {"workload": WORKLOADS["c2q"][2] + ", frames 12..%d" % (12 + fps - 1),
-           "reference_kernel_path_samples_per_s": n / (ms_ref * 1e-3), "ours_path_samples_per_s": n / (ms_ours * 1e-3),
-           "speedup": ms_ref / ms_ours,
-           "image_mean_rel_diff": float(abs(a[..., :3].mean() - b[..., :3].mean()) / a[..., :3].mean()),
-           "scatter_mean_rel_diff": float(abs(a[..., 3].mean() - b[..., 3].mean()) / a[..., 3].mean())}
-    r2.close()
-    return out
+    return run_tool([sys.executable, os.path.join(ROOT, "tools", "compare_ref_cuda.py"), "--frames", str(fps),
+                     "--device", str(device)], 240)
 
 
 if __name__ == "__main__":

@@ -94,6 +94,7 @@ static void free_volume(vp_context* c)
     dev_free(c->table);
     dev_free(c->slot_brick);
     dev_free(c->octets);
+    if (c->bounds_cell == c->bounds_voxel) c->bounds_cell = nullptr;  // shared when the fast grid is per-voxel
     dev_free(c->bounds_voxel);
     dev_free(c->bounds_cell);
     dev_free(c->top);
@@ -135,7 +136,6 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     Scene& S = c->S;
     S.nx = nx; S.ny = ny; S.nz = nz;
     S.nbx = (nx + 1 + kBrick - 1) / kBrick; S.nby = (ny + 1 + kBrick - 1) / kBrick; S.nbz = (nz + 1 + kBrick - 1) / kBrick;
-    S.ncx = (nx + 7) >> kCellLog2; S.ncy = (ny + 7) >> kCellLog2; S.ncz = (nz + 7) >> kCellLog2;
     S.voxel_type = store_voxel;
     const size_t nb = (size_t)S.nbx * S.nby * S.nbz;
     c->n_bricks     = nb;
@@ -172,6 +172,12 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     int   D         = (int)ceil(kSearchRadius / cell_size);
     c->bound_D      = D;
     const size_t N  = (size_t)nx * ny * nz;
+    // fast-renderer bound grid: cell edge = largest power of two <= max(1, D/6) voxels (<= 8)
+    int cl = 0;
+    while (cl < 3 && (2 << cl) * 6 <= D) cl++;
+    const int cell = 1 << cl;
+    S.cell_log2    = cl;
+    S.ncx = (nx + cell - 1) >> cl; S.ncy = (ny + cell - 1) >> cl; S.ncz = (nz + cell - 1) >> cl;
     if (bounds_flags & VP_BOUNDS_VOXEL)
     {
         float2* t0 = nullptr;
@@ -183,15 +189,31 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         VP_CUDA(cudaDeviceSynchronize());
         cudaFree(t0);
     }
-    if (bounds_flags & VP_BOUNDS_CELL)
+    if ((bounds_flags & VP_BOUNDS_CELL) && cell == 1)
+    {
+        if (c->bounds_voxel)
+            c->bounds_cell = c->bounds_voxel;
+        else
+        {
+            float2* t0 = nullptr;
+            VP_CUDA(cudaMalloc(&c->bounds_cell, N * sizeof(float2)));
+            VP_CUDA(cudaMalloc(&t0, N * sizeof(float2)));
+            VP_CUDA(launch_bounds_axis_f32(c->dense, c->bounds_cell, nx, ny, nz, 0, D, 1, 0));
+            VP_CUDA(launch_bounds_axis(c->bounds_cell, t0, nx, ny, nz, 1, D, 1, 0));
+            VP_CUDA(launch_bounds_axis(t0, c->bounds_cell, nx, ny, nz, 2, D, 1, 0));
+            VP_CUDA(cudaDeviceSynchronize());
+            cudaFree(t0);
+        }
+    }
+    else if (bounds_flags & VP_BOUNDS_CELL)
     {
         float2 *t0 = nullptr, *t1 = nullptr;
         VP_CUDA(cudaMalloc(&t0, (size_t)S.ncx * ny * nz * sizeof(float2)));
         VP_CUDA(cudaMalloc(&t1, (size_t)S.ncx * S.ncy * nz * sizeof(float2)));
         VP_CUDA(cudaMalloc(&c->bounds_cell, (size_t)S.ncx * S.ncy * S.ncz * sizeof(float2)));
-        VP_CUDA(launch_bounds_axis_f32(c->dense, t0, nx, ny, nz, 0, D, 8, 0));
-        VP_CUDA(launch_bounds_axis(t0, t1, S.ncx, ny, nz, 1, D, 8, 0));
-        VP_CUDA(launch_bounds_axis(t1, c->bounds_cell, S.ncx, S.ncy, nz, 2, D, 8, 0));
+        VP_CUDA(launch_bounds_axis_f32(c->dense, t0, nx, ny, nz, 0, D, cell, 0));
+        VP_CUDA(launch_bounds_axis(t0, t1, S.ncx, ny, nz, 1, D, cell, 0));
+        VP_CUDA(launch_bounds_axis(t1, c->bounds_cell, S.ncx, S.ncy, nz, 2, D, cell, 0));
         VP_CUDA(cudaDeviceSynchronize());
         cudaFree(t0);
         cudaFree(t1);
@@ -406,6 +428,7 @@ int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int fra
     }
     else if (mode == VP_MODE_FAST)
     {
+        if (!c->S.julia && !c->S.bounds_cell) return fail(VP_ERR_INVALID, "vp_render: fast mode needs VP_BOUNDS_CELL");
         // <= 512 frames per launch keeps the item counter and the per-CTA run time bounded
         for (int f = 0; f < n_frames; f += 512)
         {
@@ -507,7 +530,7 @@ int vp_volume_stats(vp_context* c, unsigned long long* out8)
     out8[4] = c->bounds_cell ? (unsigned long long)c->S.ncx * c->S.ncy * c->S.ncz * sizeof(float2) : 0;
     out8[5] = c->bounds_voxel ? (unsigned long long)c->S.nx * c->S.ny * c->S.nz * sizeof(float2) : 0;
     out8[6] = c->opacity ? (unsigned long long)c->n_slots * kOpBrickPad * sizeof(float) : 0;
-    out8[7] = (unsigned long long)c->n_bricks * 4;
+    out8[7] = (unsigned long long)(1u << c->S.cell_log2);
     return VP_OK;
 }
 int vp_rng_sequence(vp_context* c, unsigned int x, unsigned int y, unsigned int frame, int n, float* h_out_f, unsigned int* h_out_u)

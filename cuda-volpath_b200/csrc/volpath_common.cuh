@@ -24,7 +24,6 @@ namespace vp
 constexpr int      kBrickLog2   = 3;
 constexpr int      kBrick       = 1 << kBrickLog2;           // cells per brick edge
 constexpr int      kBrickCells  = kBrick * kBrick * kBrick;  // 512
-constexpr int      kCellLog2    = 3;                          // bound cells: 8^3 voxels
 constexpr int      kOpBrick     = 9 * 9 * 9;                  // opacity brick: 9^3 voxels (with apron)
 constexpr int      kOpBrickPad  = 736;                        // padded to a multiple of 32 bytes
 constexpr uint32_t kEmptyBrick  = 0xFFFFFFFFu;
@@ -44,7 +43,8 @@ struct Scene
     const uint32_t* brick_table;
     const void*     octets;
     const float2*   bounds_voxel;  // [nz][ny][nx] (max,min)   -- parity
-    const float2*   bounds_cell;   // [ncz][ncy][ncx] (max,min) -- fast
+    const float2*   bounds_cell;   // [ncz][ncy][ncx] (max,min) -- fast; cell = (1 << cell_log2)^3 voxels
+    int             cell_log2;
     const float*    opacity;       // per brick slot: 9^3 floats (+pad)
     const float4*   env;           // [env_h][env_w]
     int             env_w, env_h;

@@ -155,7 +155,7 @@ class Renderer:
         s = (ctypes.c_ulonglong * 8)()
         _l.check(self.L.vp_volume_stats(self.h, s))
         keys = ["bricks", "nonempty_bricks", "octet_bytes", "bound_radius_voxels", "bounds_cell_bytes",
-                "bounds_voxel_bytes", "opacity_bytes", "table_bytes"]
+                "bounds_voxel_bytes", "opacity_bytes", "bound_cell_voxels"]
         return dict(zip(keys, [int(v) for v in s]))
 
     def rng_sequence(self, x, y, frame, n):

@@ -1,0 +1,110 @@
+#!/usr/bin/env python3
+"""GPU tool (own process): the reference's own CUDA kernel rebuilt for sm_100 (oracle/_ref/libvolpath_ref_cuda.so)
+beside VP_MODE_FAST on the SAME scene, same GPU: path-samples/s of both, image agreement, RMSE against a high-spp
+reference image at equal spp ("matched image error").  Prints one JSON line.
+
+The reference layout needs 12 B/voxel of cudaArrays (density + float2 bounds) plus a 4 B/voxel opacity array, and its
+CPU bound sweep indexes with int, so the shared scene is the C2 cloud family at reduced dims (default 1/4: 497x338x612);
+the reference gets our device volume and our (bit-identical, tests/test_gpu_parity.py) bound volume."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dims", type=int, nargs=3, default=[497, 338, 612])
+    ap.add_argument("--image", type=int, nargs=2, default=[1920, 1080])
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--truth-frames", type=int, default=0, help="extra reference frames for an RMSE ground truth")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--density", type=float, default=800.0)
+    ap.add_argument("--albedo", type=float, default=1.0)
+    ap.add_argument("--material", type=int, default=-1, help="index into the reference's Mat() table")
+    args = ap.parse_args()
+    # the reference printf()s to stdout
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    import faulthandler
+
+    faulthandler.enable()
+    import numpy as np
+    import torch
+
+    import cuda_volpath_b200 as vp
+    from oraclelib import RefCuda
+
+    torch.cuda.set_device(args.device)
+    nx, ny, nz = args.dims
+    W, H = args.image
+    env, sd, sp = vp.default_sunsky()
+    view = vp.inv_view_matrix()
+    r = vp.Renderer(args.device)
+    r.generate_cloud(nx, ny, nz, seed=0, store=vp.VOXEL_F32, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL, keep_dense=True)
+    r.set_texture_filter_mode(True)
+    r.init_envmap(env)
+    r.set_sun(sd, sp)
+    r.copy_inv_view_matrix(view)
+    r.precompute_opacity(sd)
+    bv = torch.from_numpy(r.bounds_voxel()).cuda()
+    ref = RefCuda()
+    rc = ref.L.ref_init_volume_device(r.dense_volume_ptr(), bv.data_ptr(), nx, ny, nz, 0, None, None, 1)
+    assert rc == 0, rc
+    del bv
+    ref.dims, ref.quantized = (nx, ny, nz), False
+    ref.set_envmap(env)
+    ref.set_sun(sd, sp)
+    ref.set_inv_view(view)
+    ref.precompute_opacity(sd)
+    P = vp.default_param(W, H)
+    P.density = args.density
+    P.albedo[:] = [args.albedo] * 3
+    if args.material >= 0:
+        P = vp.mat(P, *vp.MATERIALS[args.material])
+    pa = ctypes.addressof(P)
+    stream = torch.cuda.current_stream().cuda_stream
+    warm = 12  # frames 0..11 warm both kernels up; the timed frames are all > 10 (opacity-table regime)
+    acc_r = torch.zeros(H, W, 4, device="cuda")
+    acc_o = torch.zeros(H, W, 4, device="cuda")
+    assert ref.L.ref_render_timed(acc_r.data_ptr(), 0, warm, pa) > 0
+    r.render_kernel(acc_o.data_ptr(), 0, P, mode=vp.MODE_FAST, n_frames=warm, stream=stream)
+    acc_r.zero_()
+    acc_o.zero_()
+    ms_ref = ref.L.ref_render_timed(acc_r.data_ptr(), warm, args.frames, pa)
+    assert ms_ref > 0, ms_ref
+    r.render_kernel(acc_o.data_ptr(), warm, P, mode=vp.MODE_FAST, n_frames=args.frames, stream=stream)
+    ms_ours = r.last_kernel_ms()
+    n = W * H * args.frames
+    a, b = acc_r.cpu().numpy() / args.frames, acc_o.cpu().numpy() / args.frames
+    out = {"workload": "C2 cloud family %dx%dx%d fp32, %dx%d, frames %d..%d, density %g, albedo %g, material %d"
+                       % (nx, ny, nz, W, H, warm, warm + args.frames - 1, args.density, args.albedo, args.material),
+           "reference_kernel_path_samples_per_s": n / (ms_ref * 1e-3), "ours_path_samples_per_s": n / (ms_ours * 1e-3),
+           "speedup": ms_ref / ms_ours, "ms_reference": ms_ref, "ms_ours": ms_ours,
+           "image_mean_rel_diff": float(abs(a[..., :3].mean() - b[..., :3].mean()) / a[..., :3].mean()),
+           "scatter_mean_reference": float(a[..., 3].mean()), "scatter_mean_ours": float(b[..., 3].mean())}
+    if args.truth_frames > 0:
+        t = torch.zeros(H, W, 4, device="cuda")
+        first = warm + args.frames
+        ref.L.ref_render_timed(t.data_ptr(), first, args.truth_frames, pa)
+        truth = t.cpu().numpy() / args.truth_frames
+        out["truth_frames"] = args.truth_frames
+        out["rmse_reference_vs_truth"] = float(np.sqrt(np.mean((a[..., :3] - truth[..., :3]) ** 2)))
+        out["rmse_ours_vs_truth"] = float(np.sqrt(np.mean((b[..., :3] - truth[..., :3]) ** 2)))
+        out["mean_rel_ours_vs_truth"] = float(abs(b[..., :3].mean() - truth[..., :3].mean()) / truth[..., :3].mean())
+        out["mean_rel_reference_vs_truth"] = float(abs(a[..., :3].mean() - truth[..., :3].mean()) / truth[..., :3].mean())
+    r.close()
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    print(json.dumps(out), flush=True)
+    os._exit(0)  # skip the destructors of two CUDA runtimes unloading in one process
+
+
+if __name__ == "__main__":
+    main()

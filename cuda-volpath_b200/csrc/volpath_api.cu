@@ -67,6 +67,7 @@ struct vp_context
     bool      have_volume = false;
     // instrumentation
     unsigned long long* d_stats = nullptr;
+    unsigned long long* d_work  = nullptr;  // work-pool counter of the fast renderer
     bool                stats_on = false;
     unsigned long long  launches = 0;
     cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
@@ -255,6 +256,7 @@ int vp_create(int device, vp_context** out)
     memcpy(c->inv_model, id, sizeof(id));
     VP_CUDA(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
     VP_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
     VP_CUDA(cudaEventCreate(&c->ev0));
     VP_CUDA(cudaEventCreate(&c->ev1));
     // a 1x1 black environment until init_envmap is called
@@ -272,6 +274,7 @@ int vp_destroy(vp_context* c)
     free_volume(c);
     dev_free(c->env);
     dev_free(c->d_stats);
+    dev_free(c->d_work);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -429,12 +432,15 @@ int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int fra
     else if (mode == VP_MODE_FAST)
     {
         if (!c->S.julia && !c->S.bounds_cell) return fail(VP_ERR_INVALID, "vp_render: fast mode needs VP_BOUNDS_CELL");
-        // <= 512 frames per launch keeps the item counter and the per-CTA run time bounded
-        for (int f = 0; f < n_frames; f += 512)
+        // all frames of the call are ONE launch (one work pool), as long as tiles * frames fits 31 bits
+        const long long tiles = (long long)((p->width + 7) / 8) * ((p->height + 3) / 4);
+        long long       cap   = ((1ll << 31) - 1) / tiles;
+        if (cap < 1) cap = 1;
+        for (long long f = 0; f < n_frames; f += cap)
         {
-            int nf = n_frames - f < 512 ? n_frames - f : 512;
-            VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + f * frame_stride, nf, frame_stride, *p,
-                                       c->stats_on ? c->d_stats : nullptr, st));
+            int nf = (int)(n_frames - f < cap ? n_frames - f : cap);
+            VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, c->d_work,
+                                       c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
             c->launches++;
         }
     }

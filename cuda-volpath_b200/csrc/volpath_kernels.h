@@ -14,8 +14,10 @@ cudaError_t launch_render_parity(const Scene& S, float4* d_sum, int first_frame,
                                  const vp_param& P, cudaStream_t stream);
 // d_stats: 8 device counters {track fetches, shadow fetches, segments, opacity fetches, env evaluations,
 // scatters, -, -} or nullptr (the uninstrumented kernel)
+// d_work: one device counter (the work pool of the launch); num_sms sizes the persistent grid
 cudaError_t launch_render_fast(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride,
-                               const vp_param& P, unsigned long long* d_stats, cudaStream_t stream);
+                               const vp_param& P, unsigned long long* d_work, unsigned long long* d_stats, int num_sms,
+                               cudaStream_t stream);
 cudaError_t launch_resolve(float4* dst, const float4* src, int size, float scale, float gamma, cudaStream_t stream);
 
 // --- scene build (volpath_build.cu) ---------------------------------------------------------------------

@@ -3,37 +3,48 @@
 // Same estimator as the reference's __d_render_bounded_decomp (K.cu:1958-2318) in distribution -- weighted
 // spectral delta tracking against a local majorant, analog decomposition where the local minimum is
 // positive (with the reference's quirks Q1-Q4), reduced-scattering switch after 5
-// bounces, sun NEE by shadow walk or opacity table, HG phase sampling -- re-organised for the machine:
+// bounces, sun NEE by shadow walk or opacity table, HG phase sampling -- re-organised for the machine.
+// ncu on the reference kernel rebuilt for sm_100 (profiles/r1a_ref_ncu_details.txt): 7.6 of 32 threads active
+// per warp, 20 % achieved occupancy: one thread = one pixel = one path per launch leaves the machine waiting
+// for the longest path of every warp and of every launch.  Here:
 //
-//   * a CTA owns a 16x8 pixel tile for ALL frames of the launch and keeps its float4 sums in shared memory;
-//     lanes pull (pixel, frame) items from a shared counter, so a lane whose path ended regenerates at
-//     once (no warp waits for its longest path: the reference's one-thread-one-pixel launch idles ~70 % of
-//     its lanes on clouds).  One global RMW per pixel per launch instead of one per frame.
-//   * one loop body serves both walks (primary tracking and the sun shadow walk): draw, advance, fetch,
-//     decide -- the density fetches of all 32 lanes are issued together whatever each lane is doing.
-//   * the ray is intersected with the box once; the reference's 0.05-step approach march outside the
-//     medium (Q5: ~60 of ~65 segments per path) and segments whose local max is exactly zero are skipped
-//     without random draws (an exponential walk through vacuum is memoryless: same distribution).
+//   * PERSISTENT WARPS, GLOBAL WORK POOL.  The grid is sized to the SMs; a path-sample is an item
+//     (pixel, frame) of one global index space; each warp claims ranges of 256 items with ONE atomic and hands
+//     them to lanes as they finish (ballot/popc ranking).  No lane idles before the pool is empty; nothing
+//     waits for a launch boundary (all frames of a call are one launch).
+//   * WARP-LEVEL EVENT BINNING.  A lane is in one of four states -- new path, segment setup, walk step,
+//     scatter event.  Every iteration the warp votes (match_any + redux.max) and runs ONLY the block the most
+//     lanes wait for; the others keep their state in registers.  Divergent one-lane excursions through the
+//     expensive rare blocks (HG sampling, camera setup) are replaced by batched ones.
+//   * one walk-step body serves both walks (primary tracking and the sun shadow walk): draw, advance, fetch,
+//     decide -- the density fetches of all stepping lanes are issued together.
+//   * the ray is intersected with the box once; the reference's 0.05-step approach march outside the medium
+//     (Q5: ~40 of ~59 segments per path, profiles/ref_counters.json) and segments whose local max is exactly
+//     zero are skipped without random draws (an exponential walk through vacuum is memoryless).
 //   * counter-based Philox2x32-10: key = pixel, counter = (draw index, frame); no carried RNG state.
 //   * density comes from the octet store: one table load + one 32/16/8-byte load per trilinear sample.
+//   * one vector atomic (red.global.add.v4.f32) per finished path into the float4 sum.
 #include "volpath_common.cuh"
 #include "volpath_kernels.h"
 
 namespace vp
 {
-constexpr int kTileW = 16, kTileH = 8, kTilePix = kTileW * kTileH;  // = threads per CTA
+constexpr int      kFastThreads  = 128;
+constexpr uint32_t kFull         = 0xffffffffu;
+constexpr uint32_t kClaim        = 256;  // items per warp-level claim
 
 enum : uint32_t
 {
-    kModePath  = 0,  // needs a new (pixel, frame) item
-    kModeRay   = 1,  // (o, s) set: intersect the box
-    kModeSeg   = 2,  // find the next segment with medium and set its majorants
-    kModeStep  = 3,  // walking
-    kModeIdle  = 4,  // the tile's items are exhausted: wait for the rest of the warp
+    kModeIdle  = 0,  // pool exhausted
+    kModePath  = 1,  // needs a new (pixel, frame) item
+    kModeScat  = 2,  // scattering event pending at o (direction s = incoming)
+    kModeSeg   = 3,  // find the next segment with medium and set its majorants
+    kModeStep  = 4,  // walking
     kModeMask  = 7,
     kShadow    = 8,    // walking toward the sun (else: primary tracking)
     kLimIsCtrl = 16,   // `lim` is the control-component collision distance (else: segment end)
-    kKillX = 32, kKillY = 64, kKillZ = 128,
+    kNeedRay   = 32,   // (o, s) changed: intersect the box before the next segment
+    kKillX = 64, kKillY = 128, kKillZ = 256,
 };
 
 struct Philox
@@ -73,181 +84,240 @@ __device__ __forceinline__ float hg_eval_fast(float g, float c)
     return __fdividef(1.0f - g * g, 4.0f * kPi * d * sqrtf(d));
 }
 
-template <int VT, bool JULIA, bool STATS>
-__global__ void __launch_bounds__(kTilePix) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
-                                                           int first_frame, int n_frames, int frame_stride,
-                                                           const __grid_constant__ vp_param P, int tiles_x,
-                                                           unsigned long long* __restrict__ d_stats)
+// item -> pixel: 8x4-pixel tiles, frames innermost per tile, so the 32 lanes of a fresh claim start on one tile
+__device__ __forceinline__ void item_to_sample(unsigned long long item, uint32_t n_frames, uint32_t tiles_x, uint32_t& x,
+                                               uint32_t& y, uint32_t& f)
 {
-    __shared__ float    acc[kTilePix * 4];
-    __shared__ uint32_t next_item;
-    const int           tid = threadIdx.x;
-    acc[tid * 4 + 0] = acc[tid * 4 + 1] = acc[tid * 4 + 2] = acc[tid * 4 + 3] = 0.0f;
-    if (tid == 0) next_item = kTilePix;
-    __syncthreads();
+    uint32_t p    = (uint32_t)(item & 31u);
+    uint32_t q    = (uint32_t)(item >> 5);  // the launcher keeps tiles * frames below 2^31
+    uint32_t tile = q / n_frames;
+    f             = q - tile * n_frames;
+    x = (tile % tiles_x) * 8 + (p & 7);
+    y = (tile / tiles_x) * 4 + (p >> 3);
+}
 
-    const uint32_t tile_x0 = (blockIdx.x % tiles_x) * kTileW, tile_y0 = (blockIdx.x / tiles_x) * kTileH;
-    const uint32_t n_items = (uint32_t)kTilePix * (uint32_t)n_frames;
+__device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t pix, float3 L, int n, float brightness)
+{
+    // Q9: per-sample clamp (K.cu:2315-2316); one red.global.add.v4.f32
+    float4 v = make_float4(fmaxf(L.x * brightness, 0.0f), fmaxf(L.y * brightness, 0.0f), fmaxf(L.z * brightness, 0.0f), (float)n);
+    atomicAdd(d_sum + pix, v);
+}
+
+template <int VT, bool JULIA, bool STATS>
+__global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
+                                                                  int first_frame, int n_frames, int frame_stride,
+                                                                  const __grid_constant__ vp_param P,
+                                                                  unsigned long long* __restrict__ d_work,
+                                                                  unsigned long long* __restrict__ d_stats)
+{
+    const uint32_t lane    = threadIdx.x & 31;
+    const uint32_t tiles_x = (P.width + 7) >> 3, tiles_y = (P.height + 3) >> 2;
+    const unsigned long long n_items = (unsigned long long)tiles_x * tiles_y * 32ull * (unsigned long long)n_frames;
 
     const float3 sig_t = f3(P.sigma_t.x, P.sigma_t.y, P.sigma_t.z);
     const float3 sig_s = sig_t * f3(P.albedo.x, P.albedo.y, P.albedo.z);
     const float  max_sig_t = max_of(sig_t), min_sig_t = min_of(sig_t);
 
+    // warp-uniform claim window
+    unsigned long long w_next = 0, w_end = 0;
     // lane state
     float3   o = f3(0.f), s = f3(0.f), pend = f3(0.f), T = f3(1.f), L = f3(0.f);
     float    dist = 0.f, lim = 0.f, inv = 0.f, dens = 0.f, maj = 0.f, sigc = 0.f, t_exit = 0.f, ph = 0.f, dmax = 0.f;
     int      n = 0;
-    uint32_t st = kModePath, item = tid, pslot = 0;
+    uint32_t st = kModePath, pix = 0;
     Philox   rng{0, 0, 0};
     unsigned long long c_track = 0, c_shadow = 0, c_seg = 0, c_op = 0, c_env = 0, c_scat = 0;
 
     for (;;)
     {
-        // warp-converged loop head: every lane (idle ones included) votes here, so a lane that ran out of work
-        // never leaves its warp-mates waiting at a warp-level barrier
-        if (!__any_sync(0xffffffffu, (st & kModeMask) != kModeIdle)) break;
-        if ((st & kModeMask) == kModePath)
+        // ---- vote: run the block the most lanes wait for (ties: step > segment > scatter > path) ----
+        const uint32_t mode = st & kModeMask;
+        const uint32_t same = __match_any_sync(kFull, mode);
+        const uint32_t key  = mode == kModeIdle ? 0u : ((__popc(same) << 3) | mode);
+        const uint32_t pick = __reduce_max_sync(kFull, key) & 7u;
+        if (pick == kModeIdle) break;
+
+        if (pick == kModePath)
         {
-            if (item >= n_items)
+            const uint32_t needy = __ballot_sync(kFull, mode == kModePath);
+            const uint32_t cnt = __popc(needy), rank = __popc(needy & ((1u << lane) - 1u));
+            const uint32_t avail = (uint32_t)(w_end - w_next);
+            unsigned long long item;
+            if (cnt > avail)
             {
-                st = kModeIdle;
-                continue;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(d_work, (unsigned long long)kClaim);
+                base   = __shfl_sync(kFull, base, 0);
+                item   = rank < avail ? w_next + rank : base + (rank - avail);
+                w_next = base + (cnt - avail);
+                w_end  = base + kClaim;
             }
-            pslot = item & (kTilePix - 1);
-            uint32_t f  = item >> 7;
-            uint32_t lane = pslot & 31, wrp = pslot >> 5;
-            uint32_t x = tile_x0 + (wrp & 1) * 8 + (lane & 7), y = tile_y0 + (wrp >> 1) * 4 + (lane >> 3);
-            item = atomicAdd(&next_item, 1u);
-            if (x >= P.width || y >= P.height) continue;
-            rng.key   = y * P.width + x;
-            rng.frame = (uint32_t)(first_frame + (int)f * frame_stride);
-            rng.ctr   = 0;
-            camera_ray_fast(S, x, y, P.width, P.height, o, s);
-            T = f3(1.f);
-            L = f3(0.f);
-            n  = 0;
-            st = kModeRay;
-        }
-        if ((st & kModeMask) == kModeRay)
-        {
-            // one slab test per ray (the reference repeats it every 0.05 step, K.cu:1626-1661)
-            float tn, tf;
-            box_slabs(S, o, s, tn, tf);
-            bool hit = tf > tn && tf >= 1e-3f;
-            dist   = fmaxf(tn, 0.0f);
-            t_exit = hit ? tf : -1.0f;
-            st     = kModeSeg;
-        }
-        if ((st & kModeMask) == kModeSeg)
-        {
-            bool found = false;
-            while (dist < t_exit)
+            else
             {
-                if (STATS) c_seg++;
-                float seg_end = JULIA ? t_exit : fminf(dist + kSearchRadius, t_exit);
-                float2 bnd    = JULIA ? make_float2(1.0f, 0.0f) : bounds_at(S, o + s * dist);
-                if (bnd.x <= 0.0f)
+                item = w_next + rank;
+                w_next += cnt;
+            }
+            if (mode == kModePath)
+            {
+                if (item >= n_items)
+                    st = kModeIdle;
+                else
                 {
-                    dist = seg_end;  // no medium within reach: the walk passes with probability 1
-                    continue;
-                }
-                dmax = fmaxf(1e-4f, bnd.x);
-                // reduced scattering after 5 bounces (K.cu:2039-2044)
-                float sr = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
-                dens     = ((1 - sr) + sr * (1 - P.g)) * P.density;
-                maj      = max_sig_t * dens * dmax;
-                lim      = seg_end;
-                st       = kModeStep;
-                if (bnd.y > 0.0f)  // analog decomposition (K.cu:2048-2054, Q2)
-                {
-                    float u0, u1;
-                    rng.draw(u0, u1);
-                    sigc        = min_sig_t * dens * bnd.y;
-                    float distc = dist - __fdividef(__logf(u0), fmaxf(sigc, 1e-20f));
-                    inv         = __fdividef(1.0f, fmaxf(maj - sigc, 1e-20f));
-                    if (distc < seg_end)
+                    uint32_t x, y, f;
+                    item_to_sample(item, (uint32_t)n_frames, tiles_x, x, y, f);
+                    if (x < P.width && y < P.height)
                     {
-                        lim = distc;
-                        st |= kLimIsCtrl;
+                        pix       = y * P.width + x;
+                        rng.key   = pix;
+                        rng.frame = (uint32_t)(first_frame + (int)f * frame_stride);
+                        rng.ctr   = 0;
+                        camera_ray_fast(S, x, y, P.width, P.height, o, s);
+                        T  = f3(1.f);
+                        L  = f3(0.f);
+                        n  = 0;
+                        st = kModeSeg | kNeedRay;
+                    }
+                }
+            }
+        }
+        else if (pick == kModeSeg)
+        {
+            if (mode == kModeSeg)
+            {
+                if (st & kNeedRay)
+                {
+                    // one slab test per ray (the reference repeats it every 0.05 step, K.cu:1626-1661)
+                    float tn, tf;
+                    box_slabs(S, o, s, tn, tf);
+                    dist   = fmaxf(tn, 0.0f);
+                    t_exit = (tf > tn && tf >= 1e-3f) ? tf : -1.0f;
+                }
+                bool found = false;
+                while (dist < t_exit)
+                {
+                    if (STATS) c_seg++;
+                    float  seg_end = JULIA ? t_exit : fminf(dist + kSearchRadius, t_exit);
+                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at(S, o + s * dist);
+                    if (bnd.x <= 0.0f)
+                    {
+                        dist = seg_end;  // no medium within reach: the walk passes with probability 1
+                        continue;
+                    }
+                    dmax = fmaxf(1e-4f, bnd.x);
+                    // reduced scattering after 5 bounces (K.cu:2039-2044)
+                    float sr = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
+                    dens     = ((1 - sr) + sr * (1 - P.g)) * P.density;
+                    maj      = max_sig_t * dens * dmax;
+                    lim      = seg_end;
+                    st       = kModeStep;
+                    if (bnd.y > 0.0f)  // analog decomposition (K.cu:2048-2054, Q2)
+                    {
+                        float u0, u1;
+                        rng.draw(u0, u1);
+                        sigc        = min_sig_t * dens * bnd.y;
+                        float distc = dist - __fdividef(__logf(u0), fmaxf(sigc, 1e-20f));
+                        inv         = __fdividef(1.0f, fmaxf(maj - sigc, 1e-20f));
+                        if (distc < seg_end)
+                        {
+                            lim = distc;
+                            st |= kLimIsCtrl;
+                        }
+                    }
+                    else
+                    {
+                        sigc = 0.0f;
+                        inv  = __fdividef(1.0f, maj);
+                    }
+                    found = true;
+                    break;
+                }
+                if (!found)
+                {
+                    // escaped (or never hit): environment / sun disk, then the path is complete
+                    if (STATS) c_env++;
+                    L = L + background(S, s, n) * T;
+                    accumulate(d_sum, pix, L, n, P.brightness);
+                    st = kModePath;
+                }
+            }
+        }
+        else if (pick == kModeStep)
+        {
+            if (mode == kModeStep)
+            {
+                // ---- one step of whichever walk this lane is on ----
+                float u0, u1;
+                rng.draw(u0, u1);
+                dist += -__logf(u0) * inv;
+                const bool past = dist >= lim;
+                float3     pos  = o + s * (past ? lim : dist);
+                float      den  = 0.0f;
+                if (!past)
+                {
+                    den = density_at<VT, JULIA>(S, pos) * dens;
+                    if (STATS) { if (st & kShadow) c_shadow++; else c_track++; }
+                }
+                if (st & kShadow)
+                {
+                    if (!past)
+                    {
+                        // Tr_spectral (K.cu:782-806): per-channel kill flags on one shared walk
+                        float q = den * inv;
+                        if (u1 < sig_t.x * q) st |= kKillX;
+                        if (u1 < sig_t.y * q) st |= kKillY;
+                        if (u1 < sig_t.z * q) st |= kKillZ;
+                    }
+                    if (past || (st & (kKillX | kKillY | kKillZ)) == (kKillX | kKillY | kKillZ))
+                    {
+                        float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
+                        L        = L + S.sun_power * (T * ph * a);
+                        s        = pend;
+                        st       = kModeSeg | kNeedRay;
+                        if (n >= kMaxDepth)
+                        {
+                            accumulate(d_sum, pix, L, n, P.brightness);
+                            st = kModePath;
+                        }
+                    }
+                }
+                else if (past)
+                {
+                    if (st & kLimIsCtrl)
+                    {
+                        o  = pos;  // control-component collision: no weight (Q2)
+                        st = kModeScat;
+                    }
+                    else
+                    {
+                        dist = lim;  // crossed the segment: tracking restart
+                        st   = kModeSeg;
                     }
                 }
                 else
                 {
-                    sigc = 0.0f;
-                    inv  = __fdividef(1.0f, maj);
+                    float3 t_den = sig_t * den - f3(sigc);
+                    float3 s_den = sig_s * den - f3(sigc);
+                    float3 n_den = f3(maj) - t_den;
+                    float  Ps = fabsf(t_den.x * T.x) + fabsf(t_den.y * T.y) + fabsf(t_den.z * T.z);
+                    float  Pn = fabsf(n_den.x * T.x) + fabsf(n_den.y * T.y) + fabsf(n_den.z * T.z);
+                    float  c  = Ps + Pn;
+                    float  e  = u1 * c;
+                    bool   hit = e < Ps;
+                    float  k   = __fdividef(c, maj * (hit ? Ps : Pn));
+                    T          = T * ((hit ? s_den : n_den) * k);
+                    if (hit)
+                    {
+                        o  = pos;
+                        st = kModeScat;
+                    }
                 }
-                found = true;
-                break;
-            }
-            if (!found)
-            {
-                // escaped (or never hit): environment / sun disk, then the path is complete
-                if (STATS) c_env++;
-                L = L + background(S, s, n) * T;
-                goto path_done;
             }
         }
-        if ((st & kModeMask) != kModeStep) continue;
+        else  // kModeScat
         {
-            // ---- one step of whichever walk this lane is on ----
-            float u0, u1;
-            rng.draw(u0, u1);
-            dist += -__logf(u0) * inv;
-            const bool past = dist >= lim;
-            float3     pos  = o + s * (past ? lim : dist);
-            float      den  = 0.0f;
-            if (!past)
+            if (mode == kModeScat)
             {
-                den = density_at<VT, JULIA>(S, pos) * dens;
-                if (STATS) { if (st & kShadow) c_shadow++; else c_track++; }
-            }
-            if (st & kShadow)
-            {
-                if (!past)
-                {
-                    // Tr_spectral (K.cu:782-806): per-channel kill flags on one shared walk
-                    float q = den * inv;
-                    if (u1 < sig_t.x * q) st |= kKillX;
-                    if (u1 < sig_t.y * q) st |= kKillY;
-                    if (u1 < sig_t.z * q) st |= kKillZ;
-                }
-                if (past || (st & (kKillX | kKillY | kKillZ)) == (kKillX | kKillY | kKillZ))
-                {
-                    float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
-                    L        = L + S.sun_power * (T * ph * a);
-                    s        = pend;
-                    st       = kModeRay;
-                    if (n >= kMaxDepth) goto path_done;
-                }
-                continue;
-            }
-            bool scatter;
-            if (past)
-            {
-                scatter = (st & kLimIsCtrl) != 0;  // control-component collision: no weight (Q2)
-                if (!scatter)
-                {
-                    dist = lim;  // crossed the segment: tracking restart
-                    st   = kModeSeg;
-                    continue;
-                }
-            }
-            else
-            {
-                float3 t_den = sig_t * den - f3(sigc);
-                float3 s_den = sig_s * den - f3(sigc);
-                float3 n_den = f3(maj) - t_den;
-                float  Ps = fabsf(t_den.x * T.x) + fabsf(t_den.y * T.y) + fabsf(t_den.z * T.z);
-                float  Pn = fabsf(n_den.x * T.x) + fabsf(n_den.y * T.y) + fabsf(n_den.z * T.z);
-                float  c  = Ps + Pn;
-                float  e  = u1 * c;
-                scatter   = e < Ps;
-                float k   = __fdividef(c, maj * (scatter ? Ps : Pn));
-                T         = T * ((scatter ? s_den : n_den) * k);
-                if (!scatter) continue;
-            }
-            // ---- scattering event at pos ----
-            {
+                // ---- scattering event at o, incoming direction s ----
                 if (STATS) c_scat++;
                 float sr_pre = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                 float g      = (1 - sr_pre) * P.g;  // Q4: g of the pre-increment count
@@ -259,39 +329,34 @@ __global__ void __launch_bounds__(kTilePix) k_render_fast(const __grid_constant_
                 rng.draw(r0, r1);
                 float3 l = hg_sample_local(g, r0, r1);
                 pend     = normalize3(ft * l.x + fb * l.y + s * l.z);
-                o        = pos;
                 float sr = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                 dens     = ((1 - sr) + sr * (1 - P.g)) * P.density;
                 if ((int)rng.frame > 10 && n > 20)  // K.cu:2183: precomputed sun opacity
                 {
                     if (STATS) c_op++;
-                    float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, pos, false) : 0.0f;
+                    float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, o, false) : 0.0f;
                     float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
                     L          = L + S.sun_power * (T * ph * a);
                     s          = pend;
-                    st         = kModeRay;
-                    if (n >= kMaxDepth) goto path_done;
-                    continue;
+                    st         = kModeSeg | kNeedRay;
+                    if (n >= kMaxDepth)
+                    {
+                        accumulate(d_sum, pix, L, n, P.brightness);
+                        st = kModePath;
+                    }
                 }
-                // shadow walk toward the sun with the LOCAL majorant (Q1), K.cu:2173-2208
-                inv = __fdividef(1.0f, max_sig_t * dens * dmax);
-                s   = S.sun_dir;  // normalize(sun_dir * 1e10 - pos) up to rounding
-                float tn, tf;
-                box_slabs(S, o, s, tn, tf);
-                dist = 0.0f;
-                lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
-                st   = kModeStep | kShadow;
-                continue;
+                else
+                {
+                    // shadow walk toward the sun with the LOCAL majorant (Q1), K.cu:2173-2208
+                    inv = __fdividef(1.0f, max_sig_t * dens * dmax);
+                    s   = S.sun_dir;  // normalize(sun_dir * 1e10 - pos) up to rounding
+                    float tn, tf;
+                    box_slabs(S, o, s, tn, tf);
+                    dist = 0.0f;
+                    lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
+                    st   = kModeStep | kShadow;
+                }
             }
-        }
-    path_done:
-        {
-            float* a = acc + pslot * 4;
-            atomicAdd(a + 0, fmaxf(L.x * P.brightness, 0.0f));  // Q9 clamp per sample (K.cu:2315-2316)
-            atomicAdd(a + 1, fmaxf(L.y * P.brightness, 0.0f));
-            atomicAdd(a + 2, fmaxf(L.z * P.brightness, 0.0f));
-            atomicAdd(a + 3, (float)n);
-            st = kModePath;
         }
     }
     if (STATS)
@@ -299,38 +364,33 @@ __global__ void __launch_bounds__(kTilePix) k_render_fast(const __grid_constant_
         atomicAdd(d_stats + 0, c_track); atomicAdd(d_stats + 1, c_shadow); atomicAdd(d_stats + 2, c_seg);
         atomicAdd(d_stats + 3, c_op);    atomicAdd(d_stats + 4, c_env);    atomicAdd(d_stats + 5, c_scat);
     }
-    __syncthreads();
-    {
-        uint32_t lane = tid & 31, wrp = tid >> 5;
-        uint32_t x = tile_x0 + (wrp & 1) * 8 + (lane & 7), y = tile_y0 + (wrp >> 1) * 4 + (lane >> 3);
-        if (x < P.width && y < P.height)
-        {
-            float4* p = d_sum + (x + (size_t)y * P.width);
-            float4  v = *p;
-            v.x += acc[tid * 4 + 0]; v.y += acc[tid * 4 + 1]; v.z += acc[tid * 4 + 2]; v.w += acc[tid * 4 + 3];
-            *p = v;
-        }
-    }
 }
 
 template <int VT, bool JULIA>
 static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
-                                 unsigned long long* d_stats, cudaStream_t stream)
+                                 unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
-    int tiles_x = (P.width + kTileW - 1) / kTileW, tiles_y = (P.height + kTileH - 1) / kTileH;
+    cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    // persistent grid: 8 CTAs of 128 threads per SM (64 registers/thread), never more warps than claims
+    unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
+    unsigned long long want  = (items + kClaim - 1) / kClaim;                    // warps that can get a claim
+    unsigned long long ctas  = (want + kFastThreads / 32 - 1) / (kFastThreads / 32);
+    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * 8 ? ctas : (unsigned long long)num_sms * 8);
+    if (grid < 1) grid = 1;
     if (d_stats)
-        k_render_fast<VT, JULIA, true><<<tiles_x * tiles_y, kTilePix, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, tiles_x, d_stats);
+        k_render_fast<VT, JULIA, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
     else
-        k_render_fast<VT, JULIA, false><<<tiles_x * tiles_y, kTilePix, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, tiles_x, nullptr);
+        k_render_fast<VT, JULIA, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_render_fast(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
-                               unsigned long long* d_stats, cudaStream_t stream)
+                               unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
-    if (S.julia) return launch_fast_t<kF32, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_stats, stream);
-    if (S.voxel_type == kU8) return launch_fast_t<kU8, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_stats, stream);
-    if (S.voxel_type == kF16) return launch_fast_t<kF16, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_stats, stream);
-    return launch_fast_t<kF32, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_stats, stream);
+    if (S.julia) return launch_fast_t<kF32, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
+    if (S.voxel_type == kU8) return launch_fast_t<kU8, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
+    if (S.voxel_type == kF16) return launch_fast_t<kF16, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
+    return launch_fast_t<kF32, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
 }
 }  // namespace vp

@@ -254,8 +254,8 @@ int vp_create(int device, vp_context** out)
     scene_defaults(c->S);
     const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     memcpy(c->inv_model, id, sizeof(id));
-    VP_CUDA(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
-    VP_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
     VP_CUDA(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
     VP_CUDA(cudaEventCreate(&c->ev0));
     VP_CUDA(cudaEventCreate(&c->ev1));
@@ -576,8 +576,8 @@ int vp_render_counters(vp_context* c, unsigned long long* out8, int reset)
 {
     if (!c || !out8) return fail(VP_ERR_INVALID, "bad arguments");
     VP_CUDA(cudaDeviceSynchronize());
-    VP_CUDA(cudaMemcpy(out8, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    if (reset) VP_CUDA(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMemcpy(out8, c->d_stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) VP_CUDA(cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
     return VP_OK;
 }
 int vp_last_kernel_ms(vp_context* c, float* ms)

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
     uint32_t st = kModePath, pix = 0;
     Philox   rng{0, 0, 0};
     unsigned long long c_track = 0, c_shadow = 0, c_seg = 0, c_op = 0, c_env = 0, c_scat = 0;
+    unsigned long long c_blk[4] = {0, 0, 0, 0}, c_act[4] = {0, 0, 0, 0}, c_zero_s = 0, c_zero_t = 0;
 
     for (;;)
     {
@@ -136,6 +137,12 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
         const uint32_t key  = mode == kModeIdle ? 0u : ((__popc(same) << 3) | mode);
         const uint32_t pick = __reduce_max_sync(kFull, key) & 7u;
         if (pick == kModeIdle) break;
+        if (STATS)
+        {
+            // binning efficiency: per block type, warp-level executions (lane 0) and active lanes
+            if (lane == 0) c_blk[pick - 1]++;
+            if (mode == pick) c_act[pick - 1]++;
+        }
 
         if (pick == kModePath)
         {
@@ -255,7 +262,11 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                 if (!past)
                 {
                     den = density_at<VT, JULIA>(S, pos) * dens;
-                    if (STATS) { if (st & kShadow) c_shadow++; else c_track++; }
+                    if (STATS)
+                    {
+                        if (st & kShadow) c_shadow++; else c_track++;
+                        if (den == 0.0f) { if (st & kShadow) c_zero_s++; else c_zero_t++; }
+                    }
                 }
                 if (st & kShadow)
                 {
@@ -363,6 +374,13 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
     {
         atomicAdd(d_stats + 0, c_track); atomicAdd(d_stats + 1, c_shadow); atomicAdd(d_stats + 2, c_seg);
         atomicAdd(d_stats + 3, c_op);    atomicAdd(d_stats + 4, c_env);    atomicAdd(d_stats + 5, c_scat);
+        atomicAdd(d_stats + 6, c_zero_t);
+        atomicAdd(d_stats + 7, c_zero_s);
+        for (int i = 0; i < 4; i++)
+        {
+            if (lane == 0) atomicAdd(d_stats + 8 + i, c_blk[i]);
+            atomicAdd(d_stats + 12 + i, c_act[i]);
+        }
     }
 }
 

@@ -173,10 +173,15 @@ class Renderer:
         _l.check(self.L.vp_set_stats(self.h, int(on)))
 
     def counters(self, reset=True):
-        s = (ctypes.c_ulonglong * 8)()
+        s = (ctypes.c_ulonglong * 16)()
         _l.check(self.L.vp_render_counters(self.h, s, int(reset)))
         keys = ["track_fetches", "shadow_fetches", "segments", "opacity_fetches", "env_evals", "scatters"]
-        return dict(zip(keys, [int(v) for v in s][:6]))
+        d = dict(zip(keys, [int(v) for v in s][:6]))
+        d["zero_track_fetches"], d["zero_shadow_fetches"] = int(s[6]), int(s[7])
+        # binning efficiency of the megakernel: block executions per warp and active lanes, per block type
+        for i, name in enumerate(["path", "scatter", "segment", "step"]):
+            d["blocks_" + name], d["lanes_" + name] = int(s[8 + i]), int(s[12 + i])
+        return d
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

@@ -123,8 +123,9 @@ int vp_rng_sequence(vp_context* ctx, unsigned int x, unsigned int y, unsigned in
                     unsigned int* h_out_u);                      /* reference RNG stream, from the device */
 int vp_philox2x32(vp_context* ctx, unsigned int c0, unsigned int c1, unsigned int key, unsigned int* h_out2);
 int vp_set_stats(vp_context* ctx, int enable);                   /* fast mode: run the counting kernel variant */
-int vp_render_counters(vp_context* ctx, unsigned long long* out8, int reset); /* {track fetches, shadow fetches,
-                                                                    segments, opacity fetches, env evals, scatters} */
+int vp_render_counters(vp_context* ctx, unsigned long long* out16, int reset); /* [0..5] {track fetches, shadow
+                                  fetches, segments, opacity fetches, env evals, scatters}; [8..11] warp-level block
+                                  executions {path, scatter, segment, step}; [12..15] active lanes in them */
 int vp_last_kernel_ms(vp_context* ctx, float* ms);               /* CUDA-event time of the last vp_render */
 int vp_launch_count(vp_context* ctx, unsigned long long* n);     /* kernels launched by this context */
 

@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
-    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--frames-per-step", type=int, default=64)
     ap.add_argument("--store", default="f32", choices=["f32", "f16"])
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the host reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -59,7 +59,10 @@ struct vp_context
     float2*   bounds_cell = nullptr;
     uint8_t*  top         = nullptr;
     float*    opacity     = nullptr;
+    float*    sun_clear   = nullptr;
     float4*   env         = nullptr;
+    float4*   host_acc    = nullptr;  // device accumulator of vp_render_to_host
+    size_t    host_acc_bytes = 0;
     uint32_t  n_slots     = 0;
     size_t    n_bricks    = 0;
     size_t    octet_bytes = 0;
@@ -100,6 +103,8 @@ static void free_volume(vp_context* c)
     dev_free(c->bounds_cell);
     dev_free(c->top);
     dev_free(c->opacity);
+    dev_free(c->sun_clear);
+    c->S.sun_clear = nullptr;
     c->n_slots = 0;
     c->have_volume = false;
     c->S.brick_table = nullptr;
@@ -129,6 +134,26 @@ static void set_box(vp_context* c, int nx, int ny, int nz, const float* bmin, co
     S.l_inv    = make_float3(1.0f / (S.bmax.x - S.bmin.x), 1.0f / (S.bmax.y - S.bmin.y), 1.0f / (S.bmax.z - S.bmin.z));  // K.cu:313
     S.vs_scale = make_float3(S.l_inv.x * nx, S.l_inv.y * ny, S.l_inv.z * nz);
     S.vs_off   = make_float3(-S.bmin.x * S.vs_scale.x, -S.bmin.y * S.vs_scale.y, -S.bmin.z * S.vs_scale.z);
+    S.vs_off_lin = make_float3(S.vs_off.x - 0.5f, S.vs_off.y - 0.5f, S.vs_off.z - 0.5f);
+}
+
+// (re)build the sun-clear distances of the fast renderer: needs the bound grid and the sun direction
+static int update_sun_clear(vp_context* c)
+{
+    Scene& S = c->S;
+    if (!c->have_volume || S.julia || !c->bounds_cell) return VP_OK;
+    const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
+    if (!c->sun_clear) VP_CUDA(cudaMalloc(&c->sun_clear, cells * sizeof(float)));
+    const float cell = (float)(1 << S.cell_log2);
+    const float wx = cell / S.vs_scale.x, wy = cell / S.vs_scale.y, wz = cell / S.vs_scale.z;  // world cell extents
+    const float step = 0.5f * fminf(wx, fminf(wy, wz));
+    S.sun_clear    = nullptr;
+    VP_CUDA(launch_sun_clear(S, S.sun_dir, step, c->sun_clear, 0));
+    c->launches++;
+    VP_CUDA(cudaDeviceSynchronize());
+    S.sun_clear    = c->sun_clear;
+    S.clear_margin = 0.25f * step;
+    return VP_OK;
 }
 
 // dense fp32 value volume on the device -> octet store + bound grids
@@ -230,7 +255,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     S.have_opacity = 0;
     S.julia        = 0;
     c->have_volume = true;
-    return VP_OK;
+    return update_sun_clear(c);
 }
 
 extern "C" {
@@ -275,6 +300,7 @@ int vp_destroy(vp_context* c)
     dev_free(c->env);
     dev_free(c->d_stats);
     dev_free(c->d_work);
+    dev_free(c->host_acc);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -385,7 +411,8 @@ int vp_set_sun(vp_context* c, const float* dir3, const float* power3)
     float scale = kPi * (r * r);
     S.sun_power = make_float3(S.sun_power_original.x * scale, S.sun_power_original.y * scale, S.sun_power_original.z * scale);
     S.sun_dir   = make_float3(dir3[0], dir3[1], dir3[2]);
-    return VP_OK;
+    VP_CUDA(cudaSetDevice(c->device));
+    return update_sun_clear(c);
 }
 
 int vp_set_inv_view(vp_context* c, const float* m12)
@@ -465,14 +492,17 @@ int vp_render_to_host(vp_context* c, void* h_sum, int first_frame, int n_frames,
     if (!c || !h_sum || !p) return fail(VP_ERR_INVALID, "vp_render_to_host: bad arguments");
     VP_CUDA(cudaSetDevice(c->device));
     const size_t bytes = (size_t)p->width * p->height * sizeof(float4);
-    float4*      d     = nullptr;
-    VP_CUDA(cudaMalloc(&d, bytes));
-    cudaError_t e = cudaMemcpy(d, h_sum, bytes, cudaMemcpyHostToDevice);
-    int         r = e == cudaSuccess ? vp_render(c, d, first_frame, n_frames, frame_stride, p, mode, nullptr) : (int)e;
-    if (r == 0) e = cudaMemcpy(h_sum, d, bytes, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (r != 0) return r;
-    VP_CUDA(e);
+    if (bytes > c->host_acc_bytes)
+    {
+        dev_free(c->host_acc);
+        c->host_acc_bytes = 0;
+        VP_CUDA(cudaMalloc(&c->host_acc, bytes));
+        c->host_acc_bytes = bytes;
+    }
+    VP_CUDA(cudaMemcpyAsync(c->host_acc, h_sum, bytes, cudaMemcpyHostToDevice, 0));
+    VP_TRY(vp_render(c, c->host_acc, first_frame, n_frames, frame_stride, p, mode, nullptr));
+    VP_CUDA(cudaMemcpyAsync(h_sum, c->host_acc, bytes, cudaMemcpyDeviceToHost, 0));
+    VP_CUDA(cudaStreamSynchronize(0));
     return VP_OK;
 }
 

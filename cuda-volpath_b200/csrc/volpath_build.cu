@@ -370,6 +370,42 @@ cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// sun-clear distance: per bound cell, the distance along the sun direction after which only vacuum cells
+// (bound max == 0: no medium within D voxels) follow.  A shadow walk started anywhere in the cell can stop
+// there: every later tentative collision would see zero density (exact, not an approximation).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sun_clear(const __grid_constant__ Scene S, float3 sun, float step, float* __restrict__ out)
+{
+    const size_t total = (size_t)S.ncx * S.ncy * S.ncz;
+    const float  cell  = (float)(1 << S.cell_log2);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        int    i = (int)(idx % S.ncx), j = (int)((idx / S.ncx) % S.ncy), k = (int)(idx / ((size_t)S.ncx * S.ncy));
+        float3 p = f3((fminf((i + 0.5f) * cell, (float)S.nx) - S.vs_off.x) / S.vs_scale.x,
+                      (fminf((j + 0.5f) * cell, (float)S.ny) - S.vs_off.y) / S.vs_scale.y,
+                      (fminf((k + 0.5f) * cell, (float)S.nz) - S.vs_off.z) / S.vs_scale.z);
+        float tn, tf;
+        box_slabs(S, p, sun, tn, tf);
+        float last = 0.0f;
+        for (float t = 0.0f; t < tf; t += step)
+        {
+            float3 q  = p + sun * t;
+            int    ci = clampi(__float2int_rd(fmaf(q.x, S.vs_scale.x, S.vs_off.x)), 0, S.nx - 1) >> S.cell_log2;
+            int    cj = clampi(__float2int_rd(fmaf(q.y, S.vs_scale.y, S.vs_off.y)), 0, S.ny - 1) >> S.cell_log2;
+            int    ck = clampi(__float2int_rd(fmaf(q.z, S.vs_scale.z, S.vs_off.z)), 0, S.nz - 1) >> S.cell_log2;
+            if (__ldg(S.bounds_cell + ((size_t)ck * S.ncy + cj) * S.ncx + ci).x > 0.0f) last = t;
+        }
+        out[idx] = last + step;
+    }
+}
+cudaError_t launch_sun_clear(const Scene& S, float3 sun, float step, float* out, cudaStream_t stream)
+{
+    size_t total = (size_t)S.ncx * S.ncy * S.ncz;
+    k_sun_clear<<<grid_for(total, 256, (size_t)148 * 32), 256, 0, stream>>>(S, sun, step, out);
+    return cudaGetLastError();
+}
+
 // test helper: the opacity table as a dense [nz][ny][nx] array (0 where no brick stores the voxel)
 __global__ void __launch_bounds__(256) k_gather_opacity(const __grid_constant__ Scene S, float* __restrict__ dense_out)
 {

@@ -53,6 +53,11 @@ struct Scene
     // fast renderer: world -> voxel space (p * N) as one FMA per axis, and the top-level occupancy grid
     float3          vs_scale, vs_off;
     float           cam_z;           // (float)(-1.0f / tan(54.43f * 0.00872664626)) evaluated on the host (K.cu:1981-1985)
+    // per bound cell: distance along the sun direction beyond which no medium can be met (exact vacuum clip of
+    // the shadow walk); clear_margin covers the offset between a point and its cell centre
+    const float*    sun_clear;
+    float           clear_margin;
+    float3          vs_off_lin;      // vs_off - 0.5 (texel-centre shift of the linear filter)
     const uint8_t*  top;             // [tz][ty][tx], 1 = some medium within reach of the block
     int             tx, ty, tz, top_shift;  // top cell = (8 << top_shift)... voxels per edge = 1 << top_shift
 };

@@ -59,12 +59,49 @@ struct Philox
     }
 };
 
+// density at a world position inside the box: one brick-table load + one octet load.  Positions come from
+// o + s * t with t inside the box interval, so cell' = floor(p * N - 0.5) + 1 is within [0, N] up to rounding;
+// a single unsigned range test replaces the six clamps of the texture unit's clamp addressing.
 template <int VT, bool JULIA>
 __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
 {
     if (JULIA) return julia_density(pos);
-    return fetch_density_fast<VT>(S, fmaf(pos.x, S.vs_scale.x, S.vs_off.x), fmaf(pos.y, S.vs_scale.y, S.vs_off.y),
-                                  fmaf(pos.z, S.vs_scale.z, S.vs_off.z));
+    float v[8];
+    if (!S.linear)
+    {
+        int ix = __float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)) + 1, iy = __float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)) + 1,
+            iz = __float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)) + 1;
+        ix = clampi(ix, 1, S.nx); iy = clampi(iy, 1, S.ny); iz = clampi(iz, 1, S.nz);
+        uint32_t slot = brick_slot(S, ix, iy, iz);
+        if (slot == kEmptyBrick) return 0.0f;
+        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+        return VT == kU8 ? v[0] * (1.0f / 255.0f) : v[0];
+    }
+    float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
+          zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    int   ix = (int)fx + 1, iy = (int)fy + 1, iz = (int)fz + 1;
+    if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
+    uint32_t slot = brick_slot(S, ix, iy, iz);
+    if (slot == kEmptyBrick) return 0.0f;
+    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    float a = xb - fx, b = yb - fy, g = zb - fz;
+    float c00 = fmaf(a, v[1] - v[0], v[0]);
+    float c10 = fmaf(a, v[3] - v[2], v[2]);
+    float c01 = fmaf(a, v[5] - v[4], v[4]);
+    float c11 = fmaf(a, v[7] - v[6], v[6]);
+    float c0  = fmaf(b, c10 - c00, c00);
+    float c1  = fmaf(b, c11 - c01, c01);
+    float r   = fmaf(g, c1 - c0, c0);
+    return VT == kU8 ? r * (1.0f / 255.0f) : r;
+}
+
+__device__ __forceinline__ size_t bound_cell_index(const Scene& S, float3 pos)
+{
+    int i = clampi(__float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)), 0, S.nx - 1) >> S.cell_log2;
+    int j = clampi(__float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)), 0, S.ny - 1) >> S.cell_log2;
+    int k = clampi(__float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)), 0, S.nz - 1) >> S.cell_log2;
+    return ((size_t)k * S.ncy + j) * S.ncx + i;
 }
 
 // local (max, min) at pos from the bound grid of the fast renderer: cells of (1 << cell_log2)^3 voxels, each
@@ -72,10 +109,7 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
 // than the reference's per-voxel window (and identical to it when cell_log2 == 0).
 __device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
 {
-    int i = clampi(__float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)), 0, S.nx - 1) >> S.cell_log2;
-    int j = clampi(__float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)), 0, S.ny - 1) >> S.cell_log2;
-    int k = clampi(__float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)), 0, S.nz - 1) >> S.cell_log2;
-    return __ldg(S.bounds_cell + ((size_t)k * S.ncy + j) * S.ncx + i);
+    return __ldg(S.bounds_cell + bound_cell_index(S, pos));
 }
 
 __device__ __forceinline__ float hg_eval_fast(float g, float c)
@@ -103,7 +137,7 @@ __device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t 
     atomicAdd(d_sum + pix, v);
 }
 
-template <int VT, bool JULIA, bool STATS>
+template <int VT, bool JULIA, bool GRAY, bool STATS>
 __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
@@ -242,7 +276,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                 {
                     // escaped (or never hit): environment / sun disk, then the path is complete
                     if (STATS) c_env++;
-                    L = L + background(S, s, n) * T;
+                    L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
                     accumulate(d_sum, pix, L, n, P.brightness);
                     st = kModePath;
                 }
@@ -274,14 +308,21 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                     {
                         // Tr_spectral (K.cu:782-806): per-channel kill flags on one shared walk
                         float q = den * inv;
-                        if (u1 < sig_t.x * q) st |= kKillX;
-                        if (u1 < sig_t.y * q) st |= kKillY;
-                        if (u1 < sig_t.z * q) st |= kKillZ;
+                        if (GRAY)
+                        {
+                            if (u1 < sig_t.x * q) st |= kKillX | kKillY | kKillZ;
+                        }
+                        else
+                        {
+                            if (u1 < sig_t.x * q) st |= kKillX;
+                            if (u1 < sig_t.y * q) st |= kKillY;
+                            if (u1 < sig_t.z * q) st |= kKillZ;
+                        }
                     }
                     if (past || (st & (kKillX | kKillY | kKillZ)) == (kKillX | kKillY | kKillZ))
                     {
                         float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
-                        L        = L + S.sun_power * (T * ph * a);
+                        L        = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
                         s        = pend;
                         st       = kModeSeg | kNeedRay;
                         if (n >= kMaxDepth)
@@ -302,6 +343,23 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                     {
                         dist = lim;  // crossed the segment: tracking restart
                         st   = kModeSeg;
+                    }
+                }
+                else if (GRAY)
+                {
+                    // gray medium (sigma_t and albedo equal in r, g, b): the throughput is a scalar and sum|T|
+                    // cancels out of Ps / (Ps + Pn) -- same probabilities and weights as the spectral form
+                    float t_den = sig_t.x * den - sigc;
+                    float s_den = sig_s.x * den - sigc;
+                    float n_den = maj - t_den;
+                    float at = fabsf(t_den), an = fabsf(n_den), c = at + an;
+                    bool  hit = u1 * c < at;
+                    float k   = __fdividef(c, maj * (hit ? at : an));
+                    T.x *= (hit ? s_den : n_den) * k;
+                    if (hit)
+                    {
+                        o  = pos;
+                        st = kModeScat;
                     }
                 }
                 else
@@ -347,7 +405,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                     if (STATS) c_op++;
                     float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, o, false) : 0.0f;
                     float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
-                    L          = L + S.sun_power * (T * ph * a);
+                    L          = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
                     s          = pend;
                     st         = kModeSeg | kNeedRay;
                     if (n >= kMaxDepth)
@@ -365,6 +423,8 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                     box_slabs(S, o, s, tn, tf);
                     dist = 0.0f;
                     lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
+                    // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
+                    if (!JULIA && S.sun_clear) lim = fminf(lim, __ldg(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
                     st   = kModeStep | kShadow;
                 }
             }
@@ -384,7 +444,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
     }
 }
 
-template <int VT, bool JULIA>
+template <int VT, bool JULIA, bool GRAY>
 static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
                                  unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
@@ -397,18 +457,23 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
     unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * 8 ? ctas : (unsigned long long)num_sms * 8);
     if (grid < 1) grid = 1;
     if (d_stats)
-        k_render_fast<VT, JULIA, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
+        k_render_fast<VT, JULIA, GRAY, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
     else
-        k_render_fast<VT, JULIA, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
+        k_render_fast<VT, JULIA, GRAY, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
     return cudaGetLastError();
 }
 
 cudaError_t launch_render_fast(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
                                unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
-    if (S.julia) return launch_fast_t<kF32, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
-    if (S.voxel_type == kU8) return launch_fast_t<kU8, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
-    if (S.voxel_type == kF16) return launch_fast_t<kF16, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
-    return launch_fast_t<kF32, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);
+    const bool gray = P.sigma_t.x == P.sigma_t.y && P.sigma_t.y == P.sigma_t.z && P.albedo.x == P.albedo.y && P.albedo.y == P.albedo.z;
+#define VP_FAST(VT, J)                                                                                                          \
+    return gray ? launch_fast_t<VT, J, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream) \
+                : launch_fast_t<VT, J, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)
+    if (S.julia) VP_FAST(kF32, true);
+    if (S.voxel_type == kU8) VP_FAST(kU8, false);
+    if (S.voxel_type == kF16) VP_FAST(kF16, false);
+    VP_FAST(kF32, false);
+#undef VP_FAST
 }
 }  // namespace vp

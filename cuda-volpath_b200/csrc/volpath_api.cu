@@ -204,6 +204,8 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     const int cell = 1 << cl;
     S.cell_log2    = cl;
     S.ncx = (nx + cell - 1) >> cl; S.ncy = (ny + cell - 1) >> cl; S.ncz = (nz + cell - 1) >> cl;
+    S.cs_scale = make_float3(S.vs_scale.x / cell, S.vs_scale.y / cell, S.vs_scale.z / cell);
+    S.cs_off   = make_float3(S.vs_off.x / cell, S.vs_off.y / cell, S.vs_off.z / cell);
     if (bounds_flags & VP_BOUNDS_VOXEL)
     {
         float2* t0 = nullptr;

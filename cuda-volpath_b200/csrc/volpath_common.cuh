@@ -58,6 +58,7 @@ struct Scene
     const float*    sun_clear;
     float           clear_margin;
     float3          vs_off_lin;      // vs_off - 0.5 (texel-centre shift of the linear filter)
+    float3          cs_scale, cs_off;  // world -> bound-cell space
     const uint8_t*  top;             // [tz][ty][tx], 1 = some medium within reach of the block
     int             tx, ty, tz, top_shift;  // top cell = (8 << top_shift)... voxels per edge = 1 << top_shift
 };
@@ -182,7 +183,7 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, mi
 __device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, int cz)
 {
     int bx = cx >> kBrickLog2, by = cy >> kBrickLog2, bz = cz >> kBrickLog2;
-    return __ldg(S.brick_table + ((size_t)bz * S.nby + by) * S.nbx + bx);
+    return __ldg(S.brick_table + (uint32_t)((bz * S.nby + by) * S.nbx + bx));  // < 2^31 bricks (dims <= 8184)
 }
 __device__ __forceinline__ size_t cell_in_slot(uint32_t slot, int cx, int cy, int cz)
 {
@@ -388,6 +389,35 @@ __device__ __forceinline__ void camera_ray(const Scene& S, uint32_t x, uint32_t 
     float3 dc = f3(u, v, (float)(-1.0f / tan(fovx * 0.00872664626)));
     d = normalize3(f3(dot3(dc, f3(M[0], M[1], M[2])), dot3(dc, f3(M[4], M[5], M[6])), dot3(dc, f3(M[8], M[9], M[10]))));
 }
+// fast-math variants for the production renderer (equal in distribution, not bit-for-bit)
+__device__ __forceinline__ float3 hg_sample_local_fast(float g, float rnd0, float rnd1)
+{
+    float cos_theta;
+    if (fabsf(g) > 1e-6f)
+    {
+        float s   = 2.0f * rnd0 - 1.0f;
+        float f   = __fdividef(1.0f - g * g, 1.0f + g * s);
+        cos_theta = __fdividef(0.5f, g) * (1.0f + g * g - f * f);
+        cos_theta = fmaxf(0.0f, fminf(1.0f, cos_theta));  // Q3
+    }
+    else
+    {
+        cos_theta = 2.0f * rnd0 - 1.0f;
+    }
+    float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+    float sp, cp;
+    __sincosf(2.0f * kPi * rnd1, &sp, &cp);
+    return f3(cp * sin_theta, sp * sin_theta, cos_theta);
+}
+__device__ __forceinline__ void box_slabs_fast(const Scene& S, float3 o, float3 d, float& largest_tmin, float& smallest_tmax)
+{
+    float3 invR = f3(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
+    float3 tbot = invR * (S.bmin - o);
+    float3 ttop = invR * (S.bmax - o);
+    largest_tmin  = max_of(fmin3(ttop, tbot));
+    smallest_tmax = min_of(fmax3(ttop, tbot));
+}
+
 // same ray with the per-launch constant hoisted to the host (fast renderer)
 __device__ __forceinline__ void camera_ray_fast(const Scene& S, uint32_t x, uint32_t y, uint32_t W, uint32_t H, float3& o, float3& d)
 {

@@ -30,8 +30,18 @@
 namespace vp
 {
 constexpr int      kFastThreads  = 128;
+constexpr int      kFastCtasPerSm = 9;   // 9 x 128 threads x 56 registers = 64512 of 65536
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim
+// vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a
+// lower weight makes an expensive block wait for more lanes (tuned on B200, profiles/)
+#ifndef VP_W_PATH
+#define VP_W_PATH 4
+#define VP_W_SCAT 4
+#define VP_W_SEG 4
+#define VP_W_STEP 4
+#endif
+__device__ constexpr uint32_t kPickWeight[8] = {0, VP_W_PATH, VP_W_SCAT, VP_W_SEG, VP_W_STEP, 0, 0, 0};
 
 enum : uint32_t
 {
@@ -96,12 +106,13 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     return VT == kU8 ? r * (1.0f / 255.0f) : r;
 }
 
-__device__ __forceinline__ size_t bound_cell_index(const Scene& S, float3 pos)
+__device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
 {
-    int i = clampi(__float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)), 0, S.nx - 1) >> S.cell_log2;
-    int j = clampi(__float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)), 0, S.ny - 1) >> S.cell_log2;
-    int k = clampi(__float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)), 0, S.nz - 1) >> S.cell_log2;
-    return ((size_t)k * S.ncy + j) * S.ncx + i;
+    // cell-space coordinates in one FMA per axis; the grid has < 2^31 cells
+    int i = clampi(__float2int_rd(fmaf(pos.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1);
+    int j = clampi(__float2int_rd(fmaf(pos.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1);
+    int k = clampi(__float2int_rd(fmaf(pos.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1);
+    return (uint32_t)((k * S.ncy + j) * S.ncx + i);
 }
 
 // local (max, min) at pos from the bound grid of the fast renderer: cells of (1 << cell_log2)^3 voxels, each
@@ -138,7 +149,7 @@ __device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t 
 }
 
 template <int VT, bool JULIA, bool GRAY, bool STATS>
-__global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
                                                                   unsigned long long* __restrict__ d_work,
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
         // ---- vote: run the block the most lanes wait for (ties: step > segment > scatter > path) ----
         const uint32_t mode = st & kModeMask;
         const uint32_t same = __match_any_sync(kFull, mode);
-        const uint32_t key  = mode == kModeIdle ? 0u : ((__popc(same) << 3) | mode);
+        const uint32_t key  = mode == kModeIdle ? 0u : (((__popc(same) * kPickWeight[mode]) << 3) | mode);
         const uint32_t pick = __reduce_max_sync(kFull, key) & 7u;
         if (pick == kModeIdle) break;
         if (STATS)
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                 {
                     // one slab test per ray (the reference repeats it every 0.05 step, K.cu:1626-1661)
                     float tn, tf;
-                    box_slabs(S, o, s, tn, tf);
+                    box_slabs_fast(S, o, s, tn, tf);
                     dist   = fmaxf(tn, 0.0f);
                     t_exit = (tf > tn && tf >= 1e-3f) ? tf : -1.0f;
                 }
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                 ph = hg_eval_fast(g, dot3(s, S.sun_dir));
                 float r0, r1;
                 rng.draw(r0, r1);
-                float3 l = hg_sample_local(g, r0, r1);
+                float3 l = hg_sample_local_fast(g, r0, r1);
                 pend     = normalize3(ft * l.x + fb * l.y + s * l.z);
                 float sr = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                 dens     = ((1 - sr) + sr * (1 - P.g)) * P.density;
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(kFastThreads, 8) k_render_fast(const __grid_co
                     inv = __fdividef(1.0f, max_sig_t * dens * dmax);
                     s   = S.sun_dir;  // normalize(sun_dir * 1e10 - pos) up to rounding
                     float tn, tf;
-                    box_slabs(S, o, s, tn, tf);
+                    box_slabs_fast(S, o, s, tn, tf);
                     dist = 0.0f;
                     lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
                     // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
@@ -450,11 +461,11 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
 {
     cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    // persistent grid: 8 CTAs of 128 threads per SM (64 registers/thread), never more warps than claims
+    // persistent grid: kFastCtasPerSm CTAs of 128 threads per SM, never more warps than claims
     unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
     unsigned long long want  = (items + kClaim - 1) / kClaim;                    // warps that can get a claim
     unsigned long long ctas  = (want + kFastThreads / 32 - 1) / (kFastThreads / 32);
-    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * 8 ? ctas : (unsigned long long)num_sms * 8);
+    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * kFastCtasPerSm ? ctas : (unsigned long long)num_sms * kFastCtasPerSm);
     if (grid < 1) grid = 1;
     if (d_stats)
         k_render_fast<VT, JULIA, GRAY, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);

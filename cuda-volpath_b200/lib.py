@@ -8,7 +8,7 @@ import os
 from .param import Param
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvolpath_b200.so")
+LIB_PATH = os.environ.get("VOLPATH_B200_LIB") or os.path.join(_HERE, "libvolpath_b200.so")  # override: kernel-variant experiments
 
 c_fp = ctypes.POINTER(ctypes.c_float)
 c_vp = ctypes.c_void_p

@@ -36,9 +36,9 @@ constexpr uint32_t kClaim        = 256;  // items per warp-level claim
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a
 // lower weight makes an expensive block wait for more lanes (tuned on B200, profiles/)
 #ifndef VP_W_PATH
-#define VP_W_PATH 4
-#define VP_W_SCAT 4
-#define VP_W_SEG 4
+#define VP_W_PATH 6
+#define VP_W_SCAT 6
+#define VP_W_SEG 5
 #define VP_W_STEP 4
 #endif
 __device__ constexpr uint32_t kPickWeight[8] = {0, VP_W_PATH, VP_W_SCAT, VP_W_SEG, VP_W_STEP, 0, 0, 0};
@@ -55,6 +55,7 @@ enum : uint32_t
     kLimIsCtrl = 16,   // `lim` is the control-component collision distance (else: segment end)
     kNeedRay   = 32,   // (o, s) changed: intersect the box before the next segment
     kKillX = 64, kKillY = 128, kKillZ = 256,
+    kEscaped   = 512,  // path left the medium: environment lookup + accumulate pending (done in the path block)
 };
 
 struct Philox
@@ -211,6 +212,15 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
             }
             if (mode == kModePath)
             {
+                if (st & kEscaped)
+                {
+                    // finish the previous path here, where many lanes are in the same situation: environment /
+                    // sun disk (acosf + atanf + one texel), then one vector atomic
+                    if (STATS) c_env++;
+                    L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
+                    accumulate(d_sum, pix, L, n, P.brightness);
+                    st = kModePath;
+                }
                 if (item >= n_items)
                     st = kModeIdle;
                 else
@@ -285,11 +295,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
                 }
                 if (!found)
                 {
-                    // escaped (or never hit): environment / sun disk, then the path is complete
-                    if (STATS) c_env++;
-                    L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
-                    accumulate(d_sum, pix, L, n, P.brightness);
-                    st = kModePath;
+                    st = kModePath | kEscaped;  // escaped (or never hit the box)
                 }
             }
         }

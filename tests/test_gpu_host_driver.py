@@ -1,0 +1,43 @@
+"""GPU (-m gpu): the headless C++ host (host/volpath_host.cpp) calls only the reference's 14 extern "C" entry points;
+the SAME source is linked once against libvolpath_b200.so and once against the reference kernel rebuilt for sm_100.
+Same inputs -> the dumped float4 sums must agree (point filter: 1e-5 relative on >= 98 % of pixels)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host", "volpath_host")
+HOST_REF = os.path.join(ROOT, "host", "volpath_host_ref")
+
+
+def run(binary, out, extra=()):
+    cmd = [binary, "--blob", "56", "--size", "96", "64", "--spp", "14", "--density", "300", "--dump", out] + list(extra)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "M samples / s" in p.stdout
+    return np.fromfile(out, np.float32).reshape(64, 96, 4)
+
+
+@pytest.mark.parametrize("quantized", [False, True])
+def test_cpp_host_is_a_drop_in_for_the_reference_boundary(tmp_path, quantized):
+    if not (os.path.exists(HOST) and os.path.exists(HOST_REF)):
+        pytest.skip("host binaries not built (make -C host all ref)")
+    extra = ["--point"] + (["--quantized"] if quantized else [])
+    ours = run(HOST, str(tmp_path / "ours.f32"), extra)
+    ref = run(HOST_REF, str(tmp_path / "ref.f32"), extra)
+    assert ref[..., 3].sum() > 0
+    rel = np.abs(ours - ref) / np.maximum(np.abs(ref), 1e-4)
+    assert float((rel.max(axis=-1) <= 1e-5).mean()) >= 0.98
+
+
+def test_cpp_host_fast_mode_matches_in_the_mean(tmp_path):
+    if not (os.path.exists(HOST) and os.path.exists(HOST_REF)):
+        pytest.skip("host binaries not built (make -C host all ref)")
+    cmd_extra = ["--spp", "256"]
+    fast = run(HOST, str(tmp_path / "fast.f32"), ["--fast"] + cmd_extra)
+    ref = run(HOST_REF, str(tmp_path / "ref.f32"), cmd_extra)
+    assert abs(fast[..., :3].mean() - ref[..., :3].mean()) <= 0.01 * ref[..., :3].mean()
+    assert abs(fast[..., 3].mean() - ref[..., 3].mean()) <= 0.015 * ref[..., 3].mean()

@@ -143,7 +143,7 @@ def _host_reference_run(args, julia, name):
     ref.set_sun(sun_dir, sun_power)
     ref.set_inv_view(view)
     P = vp.default_param(W, H)
-    cores = os.cpu_count() or 1
+    cores = int(os.environ.get("OMP_NUM_THREADS", "0") or 0) or (os.cpu_count() or 1)
     fps = max(1, args.ref_frames)
     acc = np.zeros((H, W, 4), np.float32)
     # frames 0..10 only: from frame 11 on the kernel reads the precomputed sun-opacity table (K.cu:2183), whose
@@ -183,6 +183,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # torchrun pins OMP_NUM_THREADS=1; the reference arm uses every host core it can
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         value, dt, cb = host_reference_run(args, desc)
         line = {"impl": "reference", "metric": "path-samples/s", "value": value, "unit": "path-samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,

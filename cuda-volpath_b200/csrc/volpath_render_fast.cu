@@ -30,7 +30,13 @@
 namespace vp
 {
 constexpr int      kFastThreads  = 128;
-constexpr int      kFastCtasPerSm = 9;   // 9 x 128 threads x 56 registers = 64512 of 65536
+#ifndef VP_CTAS_PER_SM
+#define VP_CTAS_PER_SM 9
+#endif
+#ifndef VP_STEP_REPS
+#define VP_STEP_REPS 1
+#endif
+constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;   // 9 x 128 threads x 56 registers = 64512 of 65536
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a
@@ -301,7 +307,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
         }
         else if (pick == kModeStep)
         {
-            if (mode == kModeStep)
+#pragma unroll 1
+            for (int rep = 0; rep < VP_STEP_REPS; rep++)
+            if ((st & kModeMask) == kModeStep)
             {
                 // ---- one step of whichever walk this lane is on ----
                 float u0, u1;

@@ -30,13 +30,15 @@
 namespace vp
 {
 constexpr int      kFastThreads  = 128;
+// 10 CTAs x 128 threads x 48 registers per SM (40 warps) and two walk steps per vote measured best on B200
+// (8 / 9 / 10 CTAs: 820 / 878 / 903 M path-samples/s; 1 / 2 / 3 steps per vote: 878 / 907 / 896; both: 937)
 #ifndef VP_CTAS_PER_SM
-#define VP_CTAS_PER_SM 9
+#define VP_CTAS_PER_SM 10
 #endif
 #ifndef VP_STEP_REPS
-#define VP_STEP_REPS 1
+#define VP_STEP_REPS 2
 #endif
-constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;   // 9 x 128 threads x 56 registers = 64512 of 65536
+constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a

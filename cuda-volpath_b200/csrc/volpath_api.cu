@@ -98,7 +98,6 @@ static void free_volume(vp_context* c)
     dev_free(c->table);
     dev_free(c->slot_brick);
     dev_free(c->octets);
-    if (c->bounds_cell == c->bounds_voxel) c->bounds_cell = nullptr;  // shared when the fast grid is per-voxel
     dev_free(c->bounds_voxel);
     dev_free(c->bounds_cell);
     dev_free(c->top);
@@ -219,12 +218,13 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     }
     if ((bounds_flags & VP_BOUNDS_CELL) && cell == 1)
     {
+        // always a separate array: the fast grid carries vacuum jump distances in its (negative) max field
+        VP_CUDA(cudaMalloc(&c->bounds_cell, N * sizeof(float2)));
         if (c->bounds_voxel)
-            c->bounds_cell = c->bounds_voxel;
+            VP_CUDA(cudaMemcpy(c->bounds_cell, c->bounds_voxel, N * sizeof(float2), cudaMemcpyDeviceToDevice));
         else
         {
             float2* t0 = nullptr;
-            VP_CUDA(cudaMalloc(&c->bounds_cell, N * sizeof(float2)));
             VP_CUDA(cudaMalloc(&t0, N * sizeof(float2)));
             VP_CUDA(launch_bounds_axis_f32(c->dense, c->bounds_cell, nx, ny, nz, 0, D, 1, 0));
             VP_CUDA(launch_bounds_axis(c->bounds_cell, t0, nx, ny, nz, 1, D, 1, 0));
@@ -248,6 +248,17 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     }
     VP_CUDA(cudaDeviceSynchronize());
     if (!keep_dense) dev_free(c->dense);
+    if (c->bounds_cell)
+    {
+        // vacuum jump distances (breadth-first dilation over the bound cells, up to 63 cells)
+        const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
+        uint8_t*     tmp   = nullptr;
+        VP_CUDA(cudaMalloc(&tmp, cells));
+        const float cw = fminf((float)cell / S.vs_scale.x, fminf((float)cell / S.vs_scale.y, (float)cell / S.vs_scale.z));
+        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, 63, cw, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+        cudaFree(tmp);
+    }
 
     S.brick_table  = c->table;
     S.octets       = c->octets;
@@ -525,10 +536,17 @@ int vp_get_bounds_voxel(vp_context* c, float* h_out)
 }
 int vp_get_bounds_cell(vp_context* c, float* h_out, int* dims3)
 {
+    const bool raw_jumps = dims3 && dims3[0] == -1;  // test hook: keep the encoded vacuum jumps
     if (!c || !c->bounds_cell) return fail(VP_ERR_INVALID, "no per-cell bounds");
     if (dims3) { dims3[0] = c->S.ncx; dims3[1] = c->S.ncy; dims3[2] = c->S.ncz; }
     if (h_out)
-        VP_CUDA(cudaMemcpy(h_out, c->bounds_cell, (size_t)c->S.ncx * c->S.ncy * c->S.ncz * sizeof(float2), cudaMemcpyDeviceToHost));
+    {
+        const size_t cells = (size_t)c->S.ncx * c->S.ncy * c->S.ncz;
+        VP_CUDA(cudaMemcpy(h_out, c->bounds_cell, cells * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (!raw_jumps)
+            for (size_t i = 0; i < cells; i++)
+                if (h_out[2 * i] < 0.0f) h_out[2 * i] = 0.0f;  // vacuum cells store -jump in the max field
+    }
     return VP_OK;
 }
 int vp_get_opacity(vp_context* c, float* h_out)

@@ -371,6 +371,59 @@ cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick
 }
 
 // ---------------------------------------------------------------------------------------------------
+// vacuum jump distances.  A bound cell whose max is 0 has no medium within D voxels; its chessboard distance k
+// (in cells) to the nearest cell with medium, found by breadth-first dilation, means every cell within k - 1 is
+// vacuum too, so a ray anywhere in the cell may advance 0.999 (k - 1) cell edges in ANY direction without leaving
+// vacuum.  The distance is stored in the bound grid itself as a NEGATIVE max (-jump, world units): the segment
+// loop of the fast renderer reads it with the load it does anyway.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vac_init(const float2* __restrict__ bounds, uint8_t* __restrict__ d, size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = bounds[i].x > 0.0f ? 0 : 255;
+}
+__global__ void __launch_bounds__(256) k_vac_iter(uint8_t* __restrict__ d, int ncx, int ncy, int ncz, int k)
+{
+    const size_t total = (size_t)ncx * ncy * ncz;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        if (d[idx] != 255) continue;
+        int  i = (int)(idx % ncx), j = (int)((idx / ncx) % ncy), l = (int)(idx / ((size_t)ncx * ncy));
+        bool hit = false;
+        for (int dz = -1; dz <= 1 && !hit; dz++)
+            for (int dy = -1; dy <= 1 && !hit; dy++)
+                for (int dx = -1; dx <= 1; dx++)
+                {
+                    int a = i + dx, b = j + dy, c = l + dz;
+                    if (a < 0 || b < 0 || c < 0 || a >= ncx || b >= ncy || c >= ncz) continue;
+                    // a value written in this pass is exactly k, never k - 1: in-place update is race-free
+                    if (d[((size_t)c * ncy + b) * ncx + a] == (uint8_t)(k - 1)) { hit = true; break; }
+                }
+        if (hit) d[idx] = (uint8_t)k;
+    }
+}
+__global__ void __launch_bounds__(256) k_vac_encode(float2* __restrict__ bounds, const uint8_t* __restrict__ d, size_t total, int kmax,
+                                                     float cell_world)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        int k = d[i];
+        if (k == 0) continue;
+        if (k == 255) k = kmax + 1;  // nothing within kmax cells
+        bounds[i].x = -(0.999f * (float)(k - 1) * cell_world);
+    }
+}
+cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, float cell_world,
+                                cudaStream_t stream)
+{
+    size_t total = (size_t)ncx * ncy * ncz;
+    k_vac_init<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, tmp, total);
+    for (int k = 1; k <= kmax; k++) k_vac_iter<<<grid_for(total, 256, (size_t)148 * 32), 256, 0, stream>>>(tmp, ncx, ncy, ncz, k);
+    k_vac_encode<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, tmp, total, kmax, cell_world);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // sun-clear distance: per bound cell, the distance along the sun direction after which only vacuum cells
 // (bound max == 0: no medium within D voxels) follow.  A shadow walk started anywhere in the cell can stop
 // there: every later tentative collision would see zero density (exact, not an approximation).

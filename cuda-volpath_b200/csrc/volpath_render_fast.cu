@@ -270,7 +270,9 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
                     float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at(S, o + s * dist);
                     if (bnd.x <= 0.0f)
                     {
-                        dist = seg_end;  // no medium within reach: the walk passes with probability 1
+                        // no medium within reach: the walk passes with probability 1; -bnd.x is how far it may go
+                        // in any direction without leaving vacuum (breadth-first distance over the bound cells)
+                        dist = fminf(dist + fmaxf(kSearchRadius, -bnd.x), t_exit);
                         continue;
                     }
                     dmax = fmaxf(1e-4f, bnd.x);

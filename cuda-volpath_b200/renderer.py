@@ -119,10 +119,14 @@ class Renderer:
         _l.check(self.L.vp_get_bounds_voxel(self.h, _fp(out)))
         return out
 
-    def bounds_cell(self):
+    def bounds_cell(self, raw_jumps=False):
+        """(max, min) per bound cell of the fast renderer; raw_jumps=True keeps the encoded vacuum jump distances
+        (vacuum cells hold -jump, in world units, in the max field)."""
         d = (ctypes.c_int * 3)()
         _l.check(self.L.vp_get_bounds_cell(self.h, None, d))
         out = np.empty((d[2], d[1], d[0], 2), np.float32)
+        if raw_jumps:
+            d[0] = -1
         _l.check(self.L.vp_get_bounds_cell(self.h, _fp(out), d))
         return out
 

@@ -88,6 +88,24 @@ def test_bounds_ragged_grids_vs_oracle(R, oracle, vp, dims, cell):
     assert np.array_equal(bc, want)
 
 
+def test_vacuum_jump_distances_are_conservative(R, oracle, vp):
+    """Vacuum cells of the fast bound grid carry -jump: 0.999 (k-1) cell edges with k the chessboard distance (in
+    cells) to the nearest cell with medium -- checked against scipy's exact chessboard distance transform."""
+    from scipy import ndimage
+
+    vol = small_cloud(oracle, (72, 56, 88), seed=6)
+    R.init_cuda(vol, False)
+    raw = R.bounds_cell(raw_jumps=True)[..., 0]
+    plain = R.bounds_cell()[..., 0]
+    occupied = plain > 0
+    assert occupied.any() and (~occupied).any()
+    assert np.array_equal(raw[occupied], plain[occupied]) and (raw[~occupied] <= 0).all()
+    k = ndimage.distance_transform_cdt(~occupied, metric="chessboard")  # exact distance in cells, 0 on occupied
+    cw = np.float32(2.0 / 72)  # world size of a voxel (= cell: D = 2 here)
+    want = np.float32(0.999) * (np.minimum(k, 64) - 1).astype(np.float32) * cw
+    assert np.allclose(-raw[~occupied], want[~occupied], rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("store", ["u8", "f32"])
 @pytest.mark.parametrize("linear", [False, True])
 def test_octet_store_fetch_equals_texture_emulation(R, oracle, vp, store, linear):

@@ -469,7 +469,7 @@ int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int fra
         VP_CUDA(launch_render_parity(c->S, (float4*)d_sum, first_frame, n_frames, frame_stride, *p, st));
         c->launches++;
     }
-    else if (mode == VP_MODE_FAST)
+    else if (mode == VP_MODE_FAST || mode == VP_MODE_WAVE)
     {
         if (!c->S.julia && !c->S.bounds_cell) return fail(VP_ERR_INVALID, "vp_render: fast mode needs VP_BOUNDS_CELL");
         // all frames of the call are ONE launch (one work pool), as long as tiles * frames fits 31 bits
@@ -479,8 +479,12 @@ int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int fra
         for (long long f = 0; f < n_frames; f += cap)
         {
             int nf = (int)(n_frames - f < cap ? n_frames - f : cap);
-            VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, c->d_work,
-                                       c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
+            if (mode == VP_MODE_WAVE)
+                VP_CUDA(launch_render_wave(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, c->d_work,
+                                           c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
+            else
+                VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, c->d_work,
+                                           c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
             c->launches++;
         }
     }

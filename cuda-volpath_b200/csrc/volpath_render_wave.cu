@@ -1,0 +1,538 @@
+// volpath_render_wave.cu -- VP_MODE_WAVE: the wavefront form of the production renderer, at warp scope.
+//
+// Same estimator, same Philox streams and therefore THE SAME SAMPLES as the megakernel form
+// (volpath_render_fast.cu): a (pixel, frame) item produces the same path in both.  What differs is where the ray
+// states live and how lanes are filled:
+//
+//   * every warp owns a pool of kPool = 64 ray states as structure-of-arrays in SHARED memory (29 words per
+//     state, field-major, so the 32 lanes of a batch read one field of 32 states in one LDS);
+//   * each iteration the warp picks the event type with the most waiting states (counts kept warp-uniform),
+//     COMPACTS up to 32 of them into a batch with ballot/popc ranks, loads only the fields that event needs,
+//     runs the event for the whole batch, stores only the fields it changed, and re-files the states by their
+//     new event type.  States are sorted by event type, not by lane, so the batch is full as long as the pool
+//     holds 32 states of one type: measured lanes per executed block rise from ~16 (megakernel binning, 32
+//     states per warp) towards 28+ (profiles/), at the price of ~25 shared-memory operations per event.
+//   * the work pool (one atomic per 256 items), vacuum jumps, sun-clear clip, octet fetch and the vector-atomic
+//     accumulation are those of the megakernel.
+#include "volpath_common.cuh"
+#include "volpath_kernels.h"
+
+namespace vp
+{
+namespace wave
+{
+constexpr int      kThreads = 128;
+constexpr int      kWarps   = kThreads / 32;
+constexpr int      kPool    = 64;  // ray states per warp
+constexpr int      kRows    = kPool / 32;
+constexpr uint32_t kFull    = 0xffffffffu;
+constexpr uint32_t kClaim   = 256;
+
+enum : uint32_t
+{
+    kModeIdle = 0, kModePath = 1, kModeScat = 2, kModeSeg = 3, kModeStep = 4, kModeMask = 7,
+    kShadow = 8, kLimIsCtrl = 16, kNeedRay = 32, kKillX = 64, kKillY = 128, kKillZ = 256, kEscaped = 512,
+};
+
+// state fields (one float/uint word each), field-major in the warp's pool
+enum
+{
+    F_OX, F_OY, F_OZ, F_SX, F_SY, F_SZ, F_PX, F_PY, F_PZ, F_TX, F_TY, F_TZ, F_LX, F_LY, F_LZ,
+    F_DIST, F_LIM, F_INV, F_DENS, F_MAJ, F_SIGC, F_TEXIT, F_PH, F_DMAX, F_N, F_ST, F_PIX, F_FRAME, F_CTR,
+    F_COUNT
+};
+constexpr int kWarpSmemWords = F_COUNT * kPool + kPool / 4 + 32 / 4;  // pool + mode bytes + batch bytes
+
+__device__ __forceinline__ void philox_draw(uint32_t key, uint32_t frame, uint32_t& ctr, float& u0, float& u1)
+{
+    uint32_t a, b;
+    philox2x32_10(ctr++, frame, key, a, b);
+    u0 = u32_to_unit_float(a);
+    u1 = u32_to_unit_float(b);
+}
+
+template <int VT, bool JULIA>
+__device__ __forceinline__ float density_at(const Scene& S, float3 pos)
+{
+    if (JULIA) return julia_density(pos);
+    float v[8];
+    if (!S.linear)
+    {
+        int ix = __float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)) + 1, iy = __float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)) + 1,
+            iz = __float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)) + 1;
+        ix = clampi(ix, 1, S.nx); iy = clampi(iy, 1, S.ny); iz = clampi(iz, 1, S.nz);
+        uint32_t slot = brick_slot(S, ix, iy, iz);
+        if (slot == kEmptyBrick) return 0.0f;
+        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+        return VT == kU8 ? v[0] * (1.0f / 255.0f) : v[0];
+    }
+    float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
+          zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    int   ix = (int)fx + 1, iy = (int)fy + 1, iz = (int)fz + 1;
+    if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
+    uint32_t slot = brick_slot(S, ix, iy, iz);
+    if (slot == kEmptyBrick) return 0.0f;
+    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    float a = xb - fx, b = yb - fy, g = zb - fz;
+    float c00 = fmaf(a, v[1] - v[0], v[0]);
+    float c10 = fmaf(a, v[3] - v[2], v[2]);
+    float c01 = fmaf(a, v[5] - v[4], v[4]);
+    float c11 = fmaf(a, v[7] - v[6], v[6]);
+    float c0  = fmaf(b, c10 - c00, c00);
+    float c1  = fmaf(b, c11 - c01, c01);
+    float r   = fmaf(g, c1 - c0, c0);
+    return VT == kU8 ? r * (1.0f / 255.0f) : r;
+}
+
+__device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
+{
+    int i = clampi(__float2int_rd(fmaf(pos.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1);
+    int j = clampi(__float2int_rd(fmaf(pos.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1);
+    int k = clampi(__float2int_rd(fmaf(pos.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1);
+    return (uint32_t)((k * S.ncy + j) * S.ncx + i);
+}
+
+__device__ __forceinline__ float hg_eval_fast(float g, float c)
+{
+    float d = 1.0f + g * g - 2.0f * g * c;
+    return __fdividef(1.0f - g * g, 4.0f * kPi * d * sqrtf(d));
+}
+
+__device__ __forceinline__ void item_to_sample(unsigned long long item, uint32_t n_frames, uint32_t tiles_x, uint32_t& x, uint32_t& y,
+                                               uint32_t& f)
+{
+    uint32_t p    = (uint32_t)(item & 31u);
+    uint32_t q    = (uint32_t)(item >> 5);
+    uint32_t tile = q / n_frames;
+    f             = q - tile * n_frames;
+    x = (tile % tiles_x) * 8 + (p & 7);
+    y = (tile / tiles_x) * 4 + (p >> 3);
+}
+
+__device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t pix, float3 L, int n, float brightness)
+{
+    float4 v = make_float4(fmaxf(L.x * brightness, 0.0f), fmaxf(L.y * brightness, 0.0f), fmaxf(L.z * brightness, 0.0f), (float)n);
+    atomicAdd(d_sum + pix, v);
+}
+
+#define FLD(f) pool[(f) * kPool + slot]
+#define LDF(f) FLD(f)
+#define LDU(f) __float_as_uint(FLD(f))
+#define STF(f, v) FLD(f) = (v)
+#define STU(f, v) FLD(f) = __uint_as_float(v)
+#define LD3(f) f3(FLD(f), FLD((f) + 1), FLD((f) + 2))
+#define ST3(f, v)              \
+    do {                       \
+        FLD(f)       = (v).x;  \
+        FLD((f) + 1) = (v).y;  \
+        FLD((f) + 2) = (v).z;  \
+    } while (0)
+
+template <int VT, bool JULIA, bool GRAY, bool STATS>
+__global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant__ Scene S, float4* __restrict__ d_sum, int first_frame,
+                                                          int n_frames, int frame_stride, const __grid_constant__ vp_param P,
+                                                          unsigned long long* __restrict__ d_work,
+                                                          unsigned long long* __restrict__ d_stats)
+{
+    __shared__ float smem[kWarps * kWarpSmemWords];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float*         pool  = smem + warp * kWarpSmemWords;
+    uint8_t*       modes = reinterpret_cast<uint8_t*>(pool + F_COUNT * kPool);
+    uint8_t*       batch = modes + kPool;
+
+    const uint32_t tiles_x = (P.width + 7) >> 3, tiles_y = (P.height + 3) >> 2;
+    const unsigned long long n_items = (unsigned long long)tiles_x * tiles_y * 32ull * (unsigned long long)n_frames;
+    const float3 sig_t = f3(P.sigma_t.x, P.sigma_t.y, P.sigma_t.z);
+    const float3 sig_s = sig_t * f3(P.albedo.x, P.albedo.y, P.albedo.z);
+    const float  max_sig_t = max_of(sig_t), min_sig_t = min_of(sig_t);
+
+#pragma unroll
+    for (int r = 0; r < kRows; r++)
+    {
+        modes[r * 32 + lane]                    = kModePath;
+        pool[F_ST * kPool + r * 32 + lane]      = __uint_as_float(kModePath);
+    }
+    __syncwarp();
+    // warp-uniform bookkeeping
+    unsigned long long w_next = 0, w_end = 0;
+    int cnt[5] = {0, kPool, 0, 0, 0};  // states per mode (index = mode)
+    unsigned long long c_blk[4] = {0, 0, 0, 0}, c_act[4] = {0, 0, 0, 0};
+
+    for (;;)
+    {
+        // ---- pick the event type with the most waiting states (ties: step > segment > scatter > path) ----
+        int pick = kModeIdle, best = 0;
+#pragma unroll
+        for (int m = 1; m <= 4; m++)
+            if (cnt[m] >= best && cnt[m] > 0)
+            {
+                best = cnt[m];
+                pick = m;
+            }
+        if (pick == kModeIdle) break;
+
+        // ---- compact up to 32 states of that type into a batch (ballot / popc ranks) ----
+        int base = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; r++)
+        {
+            const bool     mine = modes[r * 32 + lane] == pick;
+            const uint32_t b    = __ballot_sync(kFull, mine);
+            const int      rank = base + __popc(b & ((1u << lane) - 1u));
+            if (mine && rank < 32) batch[rank] = (uint8_t)(r * 32 + lane);
+            base += __popc(b);
+        }
+        __syncwarp();
+        const int  nb     = base < 32 ? base : 32;
+        const bool active = (int)lane < nb;
+        const int  slot   = active ? batch[lane] : 0;
+        uint32_t   st     = active ? LDU(F_ST) : kModeIdle;
+        if (STATS)
+        {
+#pragma unroll
+            for (int m = 1; m <= 4; m++)
+                if (m == pick)
+                {
+                    if (lane == 0) c_blk[m - 1]++;
+                    if (active) c_act[m - 1]++;
+                }
+        }
+
+        if (pick == kModePath)
+        {
+            // finish escaped paths, then hand out new items
+            if (active && (st & kEscaped))
+            {
+                float3 s = LD3(F_SX), T = LD3(F_TX), L = LD3(F_LX);
+                int    n = (int)LDU(F_N);
+                L        = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
+                accumulate(d_sum, LDU(F_PIX), L, n, P.brightness);
+            }
+            const uint32_t avail = (uint32_t)(w_end - w_next);
+            unsigned long long item;
+            if ((uint32_t)nb > avail)
+            {
+                unsigned long long b0 = 0;
+                if (lane == 0) b0 = atomicAdd(d_work, (unsigned long long)kClaim);
+                b0     = __shfl_sync(kFull, b0, 0);
+                item   = lane < avail ? w_next + lane : b0 + (lane - avail);
+                w_next = b0 + ((uint32_t)nb - avail);
+                w_end  = b0 + kClaim;
+            }
+            else
+            {
+                item = w_next + lane;
+                w_next += (uint32_t)nb;
+            }
+            if (active)
+            {
+                st = kModePath;
+                if (item >= n_items)
+                    st = kModeIdle;
+                else
+                {
+                    uint32_t x, y, f;
+                    item_to_sample(item, (uint32_t)n_frames, tiles_x, x, y, f);
+                    if (x < P.width && y < P.height)
+                    {
+                        float3 o, s;
+                        camera_ray_fast(S, x, y, P.width, P.height, o, s);
+                        ST3(F_OX, o);
+                        ST3(F_SX, s);
+                        ST3(F_TX, f3(1.f));
+                        ST3(F_LX, f3(0.f));
+                        STU(F_N, 0u);
+                        STU(F_PIX, y * P.width + x);
+                        STU(F_FRAME, (uint32_t)(first_frame + (int)f * frame_stride));
+                        STU(F_CTR, 0u);
+                        st = kModeSeg | kNeedRay;
+                    }
+                }
+            }
+        }
+        else if (pick == kModeSeg)
+        {
+            if (active)
+            {
+                float3 o = LD3(F_OX), s = LD3(F_SX);
+                float  dist = LDF(F_DIST), t_exit = LDF(F_TEXIT);
+                if (st & kNeedRay)
+                {
+                    float tn, tf;
+                    box_slabs_fast(S, o, s, tn, tf);
+                    dist   = fmaxf(tn, 0.0f);
+                    t_exit = (tf > tn && tf >= 1e-3f) ? tf : -1.0f;
+                    STF(F_TEXIT, t_exit);
+                }
+                bool found = false;
+                while (dist < t_exit)
+                {
+                    float  seg_end = JULIA ? t_exit : fminf(dist + kSearchRadius, t_exit);
+                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : __ldg(S.bounds_cell + bound_cell_index(S, o + s * dist));
+                    if (bnd.x <= 0.0f)
+                    {
+                        dist = fminf(dist + fmaxf(kSearchRadius, -bnd.x), t_exit);
+                        continue;
+                    }
+                    int   n    = (int)LDU(F_N);
+                    float dmax = fmaxf(1e-4f, bnd.x);
+                    float sr   = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
+                    float dens = ((1 - sr) + sr * (1 - P.g)) * P.density;
+                    float maj  = max_sig_t * dens * dmax;
+                    float lim  = seg_end, sigc, inv;
+                    st         = kModeStep;
+                    if (bnd.y > 0.0f)
+                    {
+                        uint32_t ctr = LDU(F_CTR);
+                        float    u0, u1;
+                        philox_draw(LDU(F_PIX), LDU(F_FRAME), ctr, u0, u1);
+                        STU(F_CTR, ctr);
+                        sigc        = min_sig_t * dens * bnd.y;
+                        float distc = dist - __fdividef(__logf(u0), fmaxf(sigc, 1e-20f));
+                        inv         = __fdividef(1.0f, fmaxf(maj - sigc, 1e-20f));
+                        if (distc < seg_end)
+                        {
+                            lim = distc;
+                            st |= kLimIsCtrl;
+                        }
+                    }
+                    else
+                    {
+                        sigc = 0.0f;
+                        inv  = __fdividef(1.0f, maj);
+                    }
+                    STF(F_DMAX, dmax); STF(F_DENS, dens); STF(F_MAJ, maj); STF(F_LIM, lim); STF(F_SIGC, sigc); STF(F_INV, inv);
+                    found = true;
+                    break;
+                }
+                STF(F_DIST, dist);
+                if (!found) st = kModePath | kEscaped;
+            }
+        }
+        else if (pick == kModeStep)
+        {
+            if (active)
+            {
+                float3   o = LD3(F_OX), s = LD3(F_SX);
+                float3   T = GRAY ? f3(LDF(F_TX)) : LD3(F_TX);
+                float    dist = LDF(F_DIST), lim = LDF(F_LIM), inv = LDF(F_INV), dens = LDF(F_DENS), maj = LDF(F_MAJ), sigc = LDF(F_SIGC);
+                uint32_t ctr = LDU(F_CTR);
+                const uint32_t key = LDU(F_PIX), frame = LDU(F_FRAME);
+#pragma unroll 1
+                for (int rep = 0; rep < 2 && (st & kModeMask) == kModeStep; rep++)
+                {
+                    float u0, u1;
+                    philox_draw(key, frame, ctr, u0, u1);
+                    dist += -__logf(u0) * inv;
+                    const bool past = dist >= lim;
+                    float3     pos  = o + s * (past ? lim : dist);
+                    float      den  = 0.0f;
+                    if (!past) den = density_at<VT, JULIA>(S, pos) * dens;
+                    if (st & kShadow)
+                    {
+                        if (!past)
+                        {
+                            float q = den * inv;
+                            if (GRAY)
+                            {
+                                if (u1 < sig_t.x * q) st |= kKillX | kKillY | kKillZ;
+                            }
+                            else
+                            {
+                                if (u1 < sig_t.x * q) st |= kKillX;
+                                if (u1 < sig_t.y * q) st |= kKillY;
+                                if (u1 < sig_t.z * q) st |= kKillZ;
+                            }
+                        }
+                        if (past || (st & (kKillX | kKillY | kKillZ)) == (kKillX | kKillY | kKillZ))
+                        {
+                            float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
+                            float3 L = LD3(F_LX);
+                            L        = L + S.sun_power * ((GRAY ? f3(T.x) : T) * LDF(F_PH) * a);
+                            ST3(F_LX, L);
+                            s  = LD3(F_PX);
+                            ST3(F_SX, s);
+                            st = kModeSeg | kNeedRay;
+                            int n = (int)LDU(F_N);
+                            if (n >= kMaxDepth)
+                            {
+                                accumulate(d_sum, key, L, n, P.brightness);
+                                st = kModePath;
+                            }
+                        }
+                    }
+                    else if (past)
+                    {
+                        if (st & kLimIsCtrl)
+                        {
+                            o = pos;
+                            ST3(F_OX, o);
+                            st = kModeScat;
+                        }
+                        else
+                        {
+                            dist = lim;
+                            st   = kModeSeg;
+                        }
+                    }
+                    else if (GRAY)
+                    {
+                        float t_den = sig_t.x * den - sigc;
+                        float s_den = sig_s.x * den - sigc;
+                        float n_den = maj - t_den;
+                        float at = fabsf(t_den), an = fabsf(n_den), c = at + an;
+                        bool  hit = u1 * c < at;
+                        float k   = __fdividef(c, maj * (hit ? at : an));
+                        T.x *= (hit ? s_den : n_den) * k;
+                        if (hit)
+                        {
+                            o = pos;
+                            ST3(F_OX, o);
+                            st = kModeScat;
+                        }
+                    }
+                    else
+                    {
+                        float3 t_den = sig_t * den - f3(sigc);
+                        float3 s_den = sig_s * den - f3(sigc);
+                        float3 n_den = f3(maj) - t_den;
+                        float  Ps = fabsf(t_den.x * T.x) + fabsf(t_den.y * T.y) + fabsf(t_den.z * T.z);
+                        float  Pn = fabsf(n_den.x * T.x) + fabsf(n_den.y * T.y) + fabsf(n_den.z * T.z);
+                        float  c  = Ps + Pn;
+                        bool   hit = u1 * c < Ps;
+                        float  k   = __fdividef(c, maj * (hit ? Ps : Pn));
+                        T          = T * ((hit ? s_den : n_den) * k);
+                        if (hit)
+                        {
+                            o = pos;
+                            ST3(F_OX, o);
+                            st = kModeScat;
+                        }
+                    }
+                }
+                STF(F_DIST, dist);
+                STU(F_CTR, ctr);
+                if (GRAY)
+                    STF(F_TX, T.x);
+                else
+                    ST3(F_TX, T);
+            }
+        }
+        else  // kModeScat
+        {
+            if (active)
+            {
+                float3   o = LD3(F_OX), s = LD3(F_SX);
+                float3   T = GRAY ? f3(LDF(F_TX)) : LD3(F_TX);
+                int      n = (int)LDU(F_N);
+                uint32_t ctr = LDU(F_CTR);
+                const uint32_t key = LDU(F_PIX), frame = LDU(F_FRAME);
+                float sr_pre = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
+                float g      = (1 - sr_pre) * P.g;
+                n++;
+                STU(F_N, (uint32_t)n);
+                float3 ft, fb;
+                make_frame(s, ft, fb);
+                float ph = hg_eval_fast(g, dot3(s, S.sun_dir));
+                float r0, r1;
+                philox_draw(key, frame, ctr, r0, r1);
+                STU(F_CTR, ctr);
+                float3 l    = hg_sample_local_fast(g, r0, r1);
+                float3 pend = normalize3(ft * l.x + fb * l.y + s * l.z);
+                float  sr   = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
+                float  dens = ((1 - sr) + sr * (1 - P.g)) * P.density;
+                STF(F_DENS, dens);
+                if ((int)frame > 10 && n > 20)
+                {
+                    float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, o, false) : 0.0f;
+                    float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
+                    float3 L   = LD3(F_LX);
+                    L          = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
+                    ST3(F_LX, L);
+                    ST3(F_SX, pend);
+                    st = kModeSeg | kNeedRay;
+                    if (n >= kMaxDepth)
+                    {
+                        accumulate(d_sum, key, L, n, P.brightness);
+                        st = kModePath;
+                    }
+                }
+                else
+                {
+                    float inv = __fdividef(1.0f, max_sig_t * dens * LDF(F_DMAX));
+                    s         = S.sun_dir;
+                    float tn, tf;
+                    box_slabs_fast(S, o, s, tn, tf);
+                    float lim = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
+                    if (!JULIA && S.sun_clear) lim = fminf(lim, __ldg(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
+                    STF(F_INV, inv); STF(F_LIM, lim); STF(F_DIST, 0.0f); STF(F_PH, ph);
+                    ST3(F_SX, s);
+                    ST3(F_PX, pend);
+                    st = kModeStep | kShadow;
+                }
+            }
+        }
+
+        // ---- re-file the batch by its new event types ----
+        const uint32_t nm = st & kModeMask;
+        if (active)
+        {
+            STU(F_ST, st);
+            modes[slot] = (uint8_t)nm;
+        }
+#pragma unroll
+        for (int m = 1; m <= 4; m++) cnt[m] += __popc(__ballot_sync(kFull, active && nm == (uint32_t)m)) - (m == pick ? nb : 0);
+        __syncwarp();
+    }
+    if (STATS)
+    {
+        for (int i = 0; i < 4; i++)
+        {
+            if (lane == 0) atomicAdd(d_stats + 8 + i, c_blk[i]);
+            atomicAdd(d_stats + 12 + i, c_act[i]);
+        }
+    }
+}
+}  // namespace wave
+
+template <int VT, bool JULIA, bool GRAY>
+static cudaError_t launch_wave_t(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
+                                 unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(d_work, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    if (d_stats)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::k_render_wave<VT, JULIA, GRAY, true>, wave::kThreads, 0);
+    else
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::k_render_wave<VT, JULIA, GRAY, false>, wave::kThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
+    unsigned long long want  = (items + wave::kClaim - 1) / wave::kClaim;
+    unsigned long long ctas  = (want + wave::kWarps - 1) / wave::kWarps;
+    unsigned long long cap   = (unsigned long long)num_sms * per_sm;
+    unsigned int       grid  = (unsigned int)(ctas < cap ? ctas : cap);
+    if (grid < 1) grid = 1;
+    if (d_stats)
+        wave::k_render_wave<VT, JULIA, GRAY, true><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
+    else
+        wave::k_render_wave<VT, JULIA, GRAY, false><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render_wave(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
+                               unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
+{
+    const bool gray = P.sigma_t.x == P.sigma_t.y && P.sigma_t.y == P.sigma_t.z && P.albedo.x == P.albedo.y && P.albedo.y == P.albedo.z;
+#define VP_WAVE(VT, J)                                                                                                          \
+    return gray ? launch_wave_t<VT, J, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream) \
+                : launch_wave_t<VT, J, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)
+    if (S.julia) VP_WAVE(kF32, true);
+    if (S.voxel_type == kU8) VP_WAVE(kU8, false);
+    if (S.voxel_type == kF16) VP_WAVE(kF16, false);
+    VP_WAVE(kF32, false);
+#undef VP_WAVE
+}
+}  // namespace vp

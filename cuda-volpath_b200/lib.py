@@ -20,7 +20,7 @@ VP_OK = 0
 VOXEL_U8, VOXEL_F16, VOXEL_F32 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 BOUNDS_VOXEL, BOUNDS_CELL = 1, 2
-MODE_PARITY, MODE_FAST = 0, 1
+MODE_PARITY, MODE_FAST, MODE_WAVE = 0, 1, 2
 
 
 class Float3(ctypes.Structure):

@@ -70,8 +70,10 @@ enum { VP_BOUNDS_VOXEL = 1, VP_BOUNDS_CELL = 2 };
  *   VP_MODE_PARITY : one thread per pixel, reference RNG (Wang hash + xoroshiro64*), reference draw
  *                    order and segmenting; observationally identical to render_kernel.
  *   VP_MODE_FAST   : tile-owning CTAs with per-lane path regeneration, Philox2x32-10 counter RNG, analytic
- *                    skip of the empty-space march; same estimator in distribution. */
-enum { VP_MODE_PARITY = 0, VP_MODE_FAST = 1 };
+ *                    skip of the empty-space march; same estimator in distribution.
+ *   VP_MODE_WAVE   : the wavefront form of VP_MODE_FAST: ray states as SoA pools in shared memory, batches of 32
+ *                    same-event states compacted with ballot/popc; the SAME samples as VP_MODE_FAST. */
+enum { VP_MODE_PARITY = 0, VP_MODE_FAST = 1, VP_MODE_WAVE = 2 };
 
 /* ---- (2) handle-based core -------------------------------------------------------------------- */
 const char* vp_last_error(void);                 /* message of the last failing call on this thread */

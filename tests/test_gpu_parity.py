@@ -413,3 +413,35 @@ def test_fast_counters_and_launch_count(R, oracle, vp):
     assert R.launch_count() == n0 + 1
     assert c["scatters"] == int(img[..., 3].sum())
     assert c["env_evals"] <= 64 * 48 * 4 and c["track_fetches"] > c["scatters"] > 0
+
+
+@pytest.mark.parametrize("chromatic", [False, True])
+def test_wavefront_form_renders_the_same_samples_as_the_megakernel(R, oracle, vp, chromatic):
+    """VP_MODE_WAVE keeps ray states in shared-memory pools and batches them by event type; the Philox streams are
+    addressed by (pixel, frame, draw), so every path is THE SAME path as in VP_MODE_FAST: scatter counts are equal
+    exactly, radiance up to the fp32 order of the atomic adds."""
+    vol = small_cloud(oracle, (64, 48, 80), seed=4)
+    env, sd, sp = vp.default_sunsky()
+    setup_renderer(R, vp, vol, False, True, env=env)
+    R.precompute_opacity(sd)
+    P = vp.default_param(100, 60)  # not a multiple of the 8x4 item tiles
+    P.density = 600.0
+    if chromatic:
+        P = vp.mat(P, *vp.MATERIALS[8])
+    a = R.render(P, 5, 24, mode=vp.MODE_FAST)
+    b = R.render(P, 5, 24, mode=vp.MODE_WAVE)
+    assert a[..., 3].sum() > 0 and a[..., 3].max() / 24 > 20
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert np.allclose(a[..., :3], b[..., :3], rtol=2e-5, atol=1e-6)
+
+
+def test_wavefront_form_julia(R, vp):
+    env, sd, sp = vp.default_sunsky()
+    R.set_julia()
+    R.init_envmap(env)
+    R.set_sun(sd, sp)
+    R.copy_inv_view_matrix(vp.inv_view_matrix())
+    P = vp.default_param(64, 64)
+    a = R.render(P, 0, 8, mode=vp.MODE_FAST)
+    b = R.render(P, 0, 8, mode=vp.MODE_WAVE)
+    assert np.array_equal(a[..., 3], b[..., 3]) and np.allclose(a[..., :3], b[..., :3], rtol=2e-5, atol=1e-6)

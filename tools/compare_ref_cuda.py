@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--truth-frames", type=int, default=0, help="extra reference frames for an RMSE ground truth")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--mode", default="fast", choices=["fast", "wave"])
     ap.add_argument("--density", type=float, default=800.0)
     ap.add_argument("--albedo", type=float, default=1.0)
     ap.add_argument("--material", type=int, default=-1, help="index into the reference's Mat() table")
@@ -41,6 +42,7 @@ def main():
     import cuda_volpath_b200 as vp
     from oraclelib import RefCuda
 
+    MODE = vp.MODE_WAVE if args.mode == "wave" else vp.MODE_FAST
     torch.cuda.set_device(args.device)
     nx, ny, nz = args.dims
     W, H = args.image
@@ -74,12 +76,12 @@ def main():
     acc_r = torch.zeros(H, W, 4, device="cuda")
     acc_o = torch.zeros(H, W, 4, device="cuda")
     assert ref.L.ref_render_timed(acc_r.data_ptr(), 0, warm, pa) > 0
-    r.render_kernel(acc_o.data_ptr(), 0, P, mode=vp.MODE_FAST, n_frames=warm, stream=stream)
+    r.render_kernel(acc_o.data_ptr(), 0, P, mode=MODE, n_frames=warm, stream=stream)
     acc_r.zero_()
     acc_o.zero_()
     ms_ref = ref.L.ref_render_timed(acc_r.data_ptr(), warm, args.frames, pa)
     assert ms_ref > 0, ms_ref
-    r.render_kernel(acc_o.data_ptr(), warm, P, mode=vp.MODE_FAST, n_frames=args.frames, stream=stream)
+    r.render_kernel(acc_o.data_ptr(), warm, P, mode=MODE, n_frames=args.frames, stream=stream)
     ms_ours = r.last_kernel_ms()
     n = W * H * args.frames
     a, b = acc_r.cpu().numpy() / args.frames, acc_o.cpu().numpy() / args.frames

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--dims", type=int, nargs=3, default=[497, 338, 612])
 ap.add_argument("--image", type=int, nargs=2, default=[1920, 1080])
 ap.add_argument("--frames", type=int, default=16)
+ap.add_argument("--mode", default="fast")
 a = ap.parse_args()
 import torch  # noqa: E402
 
@@ -29,7 +30,7 @@ P = vp.default_param(W, H)
 acc = torch.zeros(H, W, 4, device="cuda")
 r.set_stats(True)
 r.counters(reset=True)
-r.render_kernel(acc.data_ptr(), 16, P, mode=vp.MODE_FAST, n_frames=a.frames, stream=torch.cuda.current_stream().cuda_stream)
+r.render_kernel(acc.data_ptr(), 16, P, mode=vp.MODE_WAVE if a.mode == "wave" else vp.MODE_FAST, n_frames=a.frames, stream=torch.cuda.current_stream().cuda_stream)
 ms = r.last_kernel_ms()
 c = r.counters()
 n = W * H * a.frames

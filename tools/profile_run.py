@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--first", type=int, default=16)
     ap.add_argument("--launches", type=int, default=3)
-    ap.add_argument("--which", default="fast", choices=["fast", "parity", "ref", "julia"])
+    ap.add_argument("--which", default="fast", choices=["fast", "wave", "parity", "ref", "julia"])
     ap.add_argument("--store", default="f32")
     args = ap.parse_args()
     import torch
@@ -60,7 +60,7 @@ def main():
             ms = ref.L.ref_render_timed(acc.data_ptr(), args.first + i * args.frames, args.frames, ctypes.addressof(P))
             print("ref launch batch %d: %.3f ms, %.1f M path-samples/s" % (i, ms, W * H * args.frames / ms / 1e3), file=sys.stderr)
         os._exit(0)
-    mode = vp.MODE_PARITY if args.which == "parity" else vp.MODE_FAST
+    mode = {"parity": vp.MODE_PARITY, "wave": vp.MODE_WAVE}.get(args.which, vp.MODE_FAST)
     for i in range(args.launches):
         r.render_kernel(acc.data_ptr(), args.first + i * args.frames, P, mode=mode, n_frames=args.frames, stream=stream)
         ms = r.last_kernel_ms()

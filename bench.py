@@ -308,7 +308,11 @@ def main():
             "kernel": "k_render_fast", "kernel_ms": kernel_ms, "bytes_per_path_sample": B, "counts": cnt, "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(prof):
-        roof["traffic"] = json.load(open(prof)).get(args.workload)
+        t = json.load(open(prof)).get(args.workload)
+        if t and fps == 64 and (W, H) == (1920, 1080):
+            roof["traffic"] = t["dram_bytes_per_launch"]  # bytes per launch, same launch shape as `achieved`
+            roof["traffic_source"] = t["source"]
+        roof["algorithmic_bytes_per_launch"] = per_launch_bytes
 
     line = {"metric": "path-samples/s", "value": value, "unit": "path-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -52,7 +52,7 @@ struct vp_context
     Scene S;
     // volume
     float*    dense       = nullptr;  // dense fp32 value copy (kept on request)
-    uint32_t* table       = nullptr;
+    uint2*    words       = nullptr;  // rank directory of the octet store
     uint32_t* slot_brick  = nullptr;
     void*     octets      = nullptr;
     float2*   bounds_voxel = nullptr;
@@ -95,7 +95,7 @@ static void scene_defaults(Scene& S)
 static void free_volume(vp_context* c)
 {
     dev_free(c->dense);
-    dev_free(c->table);
+    dev_free(c->words);
     dev_free(c->slot_brick);
     dev_free(c->octets);
     dev_free(c->bounds_voxel);
@@ -106,7 +106,7 @@ static void free_volume(vp_context* c)
     c->S.sun_clear = nullptr;
     c->n_slots = 0;
     c->have_volume = false;
-    c->S.brick_table = nullptr;
+    c->S.brick_words = nullptr;
     c->S.octets = nullptr;
     c->S.bounds_voxel = nullptr;
     c->S.bounds_cell = nullptr;
@@ -179,9 +179,9 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     VP_CUDA(cudaMemcpy(&last_scan, scan + nb - 1, 4, cudaMemcpyDeviceToHost));
     VP_CUDA(cudaMemcpy(&last_flag, flags + nb - 1, 4, cudaMemcpyDeviceToHost));
     c->n_slots = last_scan + last_flag;
-    VP_CUDA(cudaMalloc(&c->table, nb * 4));
+    VP_CUDA(cudaMalloc(&c->words, ((nb + 31) / 32) * sizeof(uint2)));
     VP_CUDA(cudaMalloc(&c->slot_brick, (size_t)(c->n_slots ? c->n_slots : 1) * 4));
-    VP_CUDA(launch_make_table(flags, scan, nb, S.nbx, S.nby, c->table, c->slot_brick, 0));
+    VP_CUDA(launch_make_words(flags, scan, nb, c->words, c->slot_brick, 0));
     cudaFree(tmp);
     cudaFree(flags);
     cudaFree(scan);
@@ -260,7 +260,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         cudaFree(tmp);
     }
 
-    S.brick_table  = c->table;
+    S.brick_words  = c->words;
     S.octets       = c->octets;
     S.bounds_voxel = c->bounds_voxel;
     S.bounds_cell  = c->bounds_cell;

@@ -193,27 +193,30 @@ cudaError_t launch_classify_bricks(const float* dense, int nx, int ny, int nz, i
     return cudaGetLastError();
 }
 
-// flags + exclusive scan -> brick table (slot or kEmptyBrick) and the slot -> brick coordinate list
-__global__ void __launch_bounds__(256) k_make_table(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan,
-                                                     size_t nb, int nbx, int nby, uint32_t* __restrict__ table,
-                                                     uint32_t* __restrict__ slot_brick)
+// flags + exclusive scan -> rank directory {bits, prefix} per 32 bricks, and the slot -> brick list
+__global__ void __launch_bounds__(256) k_make_words(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan, size_t nb,
+                                                     uint2* __restrict__ words, uint32_t* __restrict__ slot_brick)
 {
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x)
+    const size_t nw = (nb + 31) / 32;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (size_t)gridDim.x * blockDim.x)
     {
-        if (flags[b])
+        uint32_t bits = 0;
+        for (int i = 0; i < 32; i++)
         {
-            uint32_t s = scan[b];
-            table[b]   = s;
-            if (slot_brick) slot_brick[s] = (uint32_t)b;
+            size_t b = w * 32 + i;
+            if (b < nb && flags[b])
+            {
+                bits |= 1u << i;
+                slot_brick[scan[b]] = (uint32_t)b;
+            }
         }
-        else
-            table[b] = kEmptyBrick;
+        words[w] = make_uint2(bits, scan[w * 32]);
     }
 }
-cudaError_t launch_make_table(const uint32_t* flags, const uint32_t* scan, size_t nb, int nbx, int nby, uint32_t* table,
-                              uint32_t* slot_brick, cudaStream_t stream)
+cudaError_t launch_make_words(const uint32_t* flags, const uint32_t* scan, size_t nb, uint2* words, uint32_t* slot_brick,
+                              cudaStream_t stream)
 {
-    k_make_table<<<grid_for(nb, 256), 256, 0, stream>>>(flags, scan, nb, nbx, nby, table, slot_brick);
+    k_make_words<<<grid_for((nb + 31) / 32, 256), 256, 0, stream>>>(flags, scan, nb, words, slot_brick);
     return cudaGetLastError();
 }
 

@@ -53,6 +53,7 @@ struct vp_context
     // volume
     float*    dense       = nullptr;  // dense fp32 value copy (kept on request)
     uint2*    words       = nullptr;  // rank directory of the octet store
+    uint32_t* table       = nullptr;  // flat slot table (small volumes only)
     uint32_t* slot_brick  = nullptr;
     void*     octets      = nullptr;
     float2*   bounds_voxel = nullptr;
@@ -96,6 +97,7 @@ static void free_volume(vp_context* c)
 {
     dev_free(c->dense);
     dev_free(c->words);
+    dev_free(c->table);
     dev_free(c->slot_brick);
     dev_free(c->octets);
     dev_free(c->bounds_voxel);
@@ -107,6 +109,7 @@ static void free_volume(vp_context* c)
     c->n_slots = 0;
     c->have_volume = false;
     c->S.brick_words = nullptr;
+    c->S.brick_table = nullptr;
     c->S.octets = nullptr;
     c->S.bounds_voxel = nullptr;
     c->S.bounds_cell = nullptr;
@@ -181,7 +184,8 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     c->n_slots = last_scan + last_flag;
     VP_CUDA(cudaMalloc(&c->words, ((nb + 31) / 32) * sizeof(uint2)));
     VP_CUDA(cudaMalloc(&c->slot_brick, (size_t)(c->n_slots ? c->n_slots : 1) * 4));
-    VP_CUDA(launch_make_words(flags, scan, nb, c->words, c->slot_brick, 0));
+    if (nb * 4 <= (size_t)4 << 20) VP_CUDA(cudaMalloc(&c->table, nb * 4));  // <= 4 MB: stays cache-resident
+    VP_CUDA(launch_make_words(flags, scan, nb, c->words, c->slot_brick, c->table, 0));
     cudaFree(tmp);
     cudaFree(flags);
     cudaFree(scan);
@@ -261,6 +265,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     }
 
     S.brick_words  = c->words;
+    S.brick_table  = c->table;
     S.octets       = c->octets;
     S.bounds_voxel = c->bounds_voxel;
     S.bounds_cell  = c->bounds_cell;

@@ -195,7 +195,8 @@ cudaError_t launch_classify_bricks(const float* dense, int nx, int ny, int nz, i
 
 // flags + exclusive scan -> rank directory {bits, prefix} per 32 bricks, and the slot -> brick list
 __global__ void __launch_bounds__(256) k_make_words(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ scan, size_t nb,
-                                                     uint2* __restrict__ words, uint32_t* __restrict__ slot_brick)
+                                                     uint2* __restrict__ words, uint32_t* __restrict__ slot_brick,
+                                                     uint32_t* __restrict__ table)
 {
     const size_t nw = (nb + 31) / 32;
     for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (size_t)gridDim.x * blockDim.x)
@@ -204,19 +205,21 @@ __global__ void __launch_bounds__(256) k_make_words(const uint32_t* __restrict__
         for (int i = 0; i < 32; i++)
         {
             size_t b = w * 32 + i;
-            if (b < nb && flags[b])
+            if (b >= nb) break;
+            if (flags[b])
             {
                 bits |= 1u << i;
                 slot_brick[scan[b]] = (uint32_t)b;
             }
+            if (table) table[b] = flags[b] ? scan[b] : kEmptyBrick;
         }
         words[w] = make_uint2(bits, scan[w * 32]);
     }
 }
 cudaError_t launch_make_words(const uint32_t* flags, const uint32_t* scan, size_t nb, uint2* words, uint32_t* slot_brick,
-                              cudaStream_t stream)
+                              uint32_t* table, cudaStream_t stream)
 {
-    k_make_words<<<grid_for((nb + 31) / 32, 256), 256, 0, stream>>>(flags, scan, nb, words, slot_brick);
+    k_make_words<<<grid_for((nb + 31) / 32, 256), 256, 0, stream>>>(flags, scan, nb, words, slot_brick, table);
     return cudaGetLastError();
 }
 

@@ -41,6 +41,7 @@ struct Scene
     int    voxel_type, linear, julia, have_opacity;
     float3 bmin, bmax, l_inv;  // K.cu:155-159 (min, max, 1/(max-min))
     const uint2*    brick_words;   // per 32 bricks (x-fastest order): {occupancy bits, slot of the first set bit}
+    const uint32_t* brick_table;   // flat slot table, kept only while it is small enough to live in L1/L2 (else null)
     const void*     octets;
     const float2*   bounds_voxel;  // [nz][ny][nx] (max,min)   -- parity
     const float2*   bounds_cell;   // [ncz][ncy][ncx] (max,min) -- fast; cell = (1 << cell_log2)^3 voxels
@@ -187,6 +188,7 @@ __device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, i
     // slot = prefix(word) + popc(bits below).  8 bytes per 32 bricks (C2: 3.2 MB instead of 52 MB) -- the first of
     // the two dependent loads of a density fetch now hits L1/L2 instead of competing with the octets for L2.
     const uint32_t b   = (uint32_t)((bz * S.nby + by) * S.nbx + bx);  // < 2^31 bricks (dims <= 8184)
+    if (S.brick_table) return __ldg(S.brick_table + b);  // small volumes: 4 MB of flat table is cache-resident anyway
     const uint2    w   = __ldg(S.brick_words + (b >> 5));
     const uint32_t bit = 1u << (b & 31u);
     return (w.x & bit) ? w.y + __popc(w.x & (bit - 1u)) : kEmptyBrick;

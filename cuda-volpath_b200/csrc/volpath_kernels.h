@@ -36,7 +36,7 @@ cudaError_t launch_bounds_axis(const float2* in, float2* out, int n0, int n1, in
 cudaError_t launch_classify_bricks(const float* dense, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* flags,
                                    cudaStream_t stream);
 cudaError_t launch_make_words(const uint32_t* flags, const uint32_t* scan, size_t nb, uint2* words, uint32_t* slot_brick,
-                              cudaStream_t stream);
+                              uint32_t* table, cudaStream_t stream);
 cudaError_t launch_fill_octets(const float* dense, int nx, int ny, int nz, int nbx, int nby, const uint32_t* slot_brick,
                                uint32_t n_slots, void* pool, int voxel_type, cudaStream_t stream);
 cudaError_t launch_top_grid(const float2* bounds_cell, int ncx, int ncy, int ncz, uint8_t* top, int tx, int ty, int tz,

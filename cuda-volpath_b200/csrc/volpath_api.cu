@@ -58,7 +58,6 @@ struct vp_context
     void*     octets      = nullptr;
     float2*   bounds_voxel = nullptr;
     float2*   bounds_cell = nullptr;
-    uint8_t*  top         = nullptr;
     float*    opacity     = nullptr;
     float*    sun_clear   = nullptr;
     float4*   env         = nullptr;
@@ -102,7 +101,6 @@ static void free_volume(vp_context* c)
     dev_free(c->octets);
     dev_free(c->bounds_voxel);
     dev_free(c->bounds_cell);
-    dev_free(c->top);
     dev_free(c->opacity);
     dev_free(c->sun_clear);
     c->S.sun_clear = nullptr;
@@ -114,7 +112,6 @@ static void free_volume(vp_context* c)
     c->S.bounds_voxel = nullptr;
     c->S.bounds_cell = nullptr;
     c->S.opacity = nullptr;
-    c->S.top = nullptr;
     c->S.have_opacity = 0;
     c->S.julia = 0;
 }

@@ -291,36 +291,6 @@ cudaError_t launch_fill_octets(const float* dense, int nx, int ny, int nz, int n
     return cudaGetLastError();
 }
 
-// top-level occupancy: one byte per (cells_per_top)^3 block of bound cells, 1 if any cell's max > 0.
-// Because a bound cell's max covers the cell +-D voxels, top == 0 means the density is zero within D voxels
-// (>= search_radius) of every point of the block: whole 0.05-segments starting there see no medium.
-__global__ void __launch_bounds__(256) k_top_grid(const float2* __restrict__ bounds_cell, int ncx, int ncy, int ncz,
-                                                   uint8_t* __restrict__ top, int tx, int ty, int tz, int cpt)
-{
-    size_t total = (size_t)tx * ty * tz;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
-    {
-        int  ix = (int)(idx % tx), iy = (int)((idx / tx) % ty), iz = (int)(idx / ((size_t)tx * ty));
-        bool any = false;
-        for (int k = iz * cpt; k < min(ncz, iz * cpt + cpt) && !any; k++)
-            for (int j = iy * cpt; j < min(ncy, iy * cpt + cpt) && !any; j++)
-                for (int i = ix * cpt; i < min(ncx, ix * cpt + cpt); i++)
-                    if (bounds_cell[((size_t)k * ncy + j) * ncx + i].x > 0.0f)
-                    {
-                        any = true;
-                        break;
-                    }
-        top[idx] = any ? 1 : 0;
-    }
-}
-cudaError_t launch_top_grid(const float2* bounds_cell, int ncx, int ncy, int ncz, uint8_t* top, int tx, int ty, int tz,
-                            int cells_per_top, cudaStream_t stream)
-{
-    size_t total = (size_t)tx * ty * tz;
-    k_top_grid<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, ncx, ncy, ncz, top, tx, ty, tz, cells_per_top);
-    return cudaGetLastError();
-}
-
 // ---------------------------------------------------------------------------------------------------
 // precomputed sun opacity (K.cu:483-553): per voxel, the Riemann sum of the (filtered) density toward the
 // sun with dt = 0.001 up to the box exit -- the same float sequence as the reference (t += dt, opacity +=
@@ -333,6 +303,8 @@ __global__ void __launch_bounds__(256) k_precompute_opacity(const __grid_constan
 {
     const float  dt    = 0.001f;
     const size_t total = (size_t)n_slots * 729;
+    const float  inv_len = rsqrtf(dot3(light_dir, light_dir));
+    const bool   use_clear = S.sun_clear && light_dir.x == S.sun_dir.x && light_dir.y == S.sun_dir.y && light_dir.z == S.sun_dir.z;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
     {
         uint32_t s = (uint32_t)(idx / 729);
@@ -351,10 +323,34 @@ __global__ void __launch_bounds__(256) k_precompute_opacity(const __grid_constan
         float opacity = 0.0f;
         if (hit)
         {
+            // Exact shortcuts (the float sequence of tt and of the sum is unchanged, adding 0.0f is the identity):
+            //  * beyond the sun-clear distance of the start cell every sample is zero -> stop there;
+            //  * inside a vacuum bound cell the next floor(jump / dt) samples are zero -> advance tt only.
+            if (use_clear)
+            {
+                int ci = clampi(__float2int_rd(fmaf(start.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1);
+                int cj = clampi(__float2int_rd(fmaf(start.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1);
+                int ck = clampi(__float2int_rd(fmaf(start.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1);
+                tf     = fminf(tf, __ldg(S.sun_clear + ((size_t)ck * S.ncy + cj) * S.ncx + ci) + S.clear_margin);
+            }
             for (float tt = tn; tt < tf; tt += dt)
             {
                 float3 pos = start + light_dir * tt;
-                opacity += fetch_density_parity<VT>(S, pos);
+                float  v   = fetch_density_parity<VT>(S, pos);
+                opacity += v;
+                if (v == 0.0f && S.bounds_cell)
+                {
+                    int   ci = clampi(__float2int_rd(fmaf(pos.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1);
+                    int   cj = clampi(__float2int_rd(fmaf(pos.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1);
+                    int   ck = clampi(__float2int_rd(fmaf(pos.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1);
+                    float cmax = __ldg(S.bounds_cell + ((size_t)ck * S.ncy + cj) * S.ncx + ci).x;
+                    if (cmax < 0.0f)
+                    {
+                        // -cmax = distance that stays in vacuum in any direction; |light_dir| may differ from 1
+                        int n = (int)(-cmax * inv_len / dt) - 2;
+                        for (; n > 0 && tt + dt < tf; n--) tt += dt;
+                    }
+                }
             }
             opacity *= dt;
         }

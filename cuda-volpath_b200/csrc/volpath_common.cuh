@@ -51,7 +51,7 @@ struct Scene
     int             env_w, env_h;
     float3          sun_dir, sun_power, sun_power_original;  // K.cu:1254-1256
     float           inv_view[12];                            // K.cu:626
-    // fast renderer: world -> voxel space (p * N) as one FMA per axis, and the top-level occupancy grid
+    // fast renderer: world -> voxel space (p * N) as one FMA per axis
     float3          vs_scale, vs_off;
     float           cam_z;           // (float)(-1.0f / tan(54.43f * 0.00872664626)) evaluated on the host (K.cu:1981-1985)
     // per bound cell: distance along the sun direction beyond which no medium can be met (exact vacuum clip of
@@ -60,8 +60,6 @@ struct Scene
     float           clear_margin;
     float3          vs_off_lin;      // vs_off - 0.5 (texel-centre shift of the linear filter)
     float3          cs_scale, cs_off;  // world -> bound-cell space
-    const uint8_t*  top;             // [tz][ty][tx], 1 = some medium within reach of the block
-    int             tx, ty, tz, top_shift;  // top cell = (8 << top_shift)... voxels per edge = 1 << top_shift
 };
 
 // ---- float3 helpers (operation order of src/cuda/helper_math.h) --------------------------------

@@ -39,8 +39,6 @@ cudaError_t launch_make_words(const uint32_t* flags, const uint32_t* scan, size_
                               uint32_t* table, cudaStream_t stream);
 cudaError_t launch_fill_octets(const float* dense, int nx, int ny, int nz, int nbx, int nby, const uint32_t* slot_brick,
                                uint32_t n_slots, void* pool, int voxel_type, cudaStream_t stream);
-cudaError_t launch_top_grid(const float2* bounds_cell, int ncx, int ncy, int ncz, uint8_t* top, int tx, int ty, int tz,
-                            int cells_per_top, cudaStream_t stream);
 cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick, uint32_t n_slots, float* opacity_bricks,
                                       float3 light_dir, cudaStream_t stream);
 cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, float cell_world,

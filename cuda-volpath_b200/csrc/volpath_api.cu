@@ -67,6 +67,7 @@ struct vp_context
     size_t    n_bricks    = 0;
     size_t    octet_bytes = 0;
     int       bound_D     = 0;
+    int       vac_margin  = 0;
     bool      have_volume = false;
     // instrumentation
     unsigned long long* d_stats = nullptr;
@@ -255,8 +256,16 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
         uint8_t*     tmp   = nullptr;
         VP_CUDA(cudaMalloc(&tmp, cells));
-        const float cw = fminf((float)cell / S.vs_scale.x, fminf((float)cell / S.vs_scale.y, (float)cell / S.vs_scale.z));
-        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, 63, cw, 0));
+        // world sizes: a voxel per axis, the smallest cell edge, what the +-D window covers at least, and what a 0.05
+        // segment plus the trilinear footprint (and a voxel of slack) needs; the deficit becomes the fringe margin
+        const float vx = 1.0f / S.vs_scale.x, vy = 1.0f / S.vs_scale.y, vz = 1.0f / S.vs_scale.z;
+        const float cw = (float)cell * fminf(vx, fminf(vy, vz));
+        const float cover  = (float)D * fminf(vx, fminf(vy, vz));
+        const float need   = kSearchRadius + 2.0f * fmaxf(vx, fmaxf(vy, vz));
+        int         margin = need > cover ? (int)ceilf((need - cover) / cw) : 0;
+        if (margin > 32) margin = 32;
+        c->vac_margin = margin;
+        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, 63, margin, cw, 0));
         VP_CUDA(cudaDeviceSynchronize());
         cudaFree(tmp);
     }
@@ -551,7 +560,7 @@ int vp_get_bounds_cell(vp_context* c, float* h_out, int* dims3)
         VP_CUDA(cudaMemcpy(h_out, c->bounds_cell, cells * sizeof(float2), cudaMemcpyDeviceToHost));
         if (!raw_jumps)
             for (size_t i = 0; i < cells; i++)
-                if (h_out[2 * i] < 0.0f) h_out[2 * i] = 0.0f;  // vacuum cells store -jump in the max field
+                if (h_out[2 * i] < 1e-20f) h_out[2 * i] = 0.0f;  // vacuum cells store -jump (fringe: 1e-30) in the max field
     }
     return VP_OK;
 }

@@ -375,8 +375,8 @@ cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick
 // ---------------------------------------------------------------------------------------------------
 // vacuum jump distances.  A bound cell whose max is 0 has no medium within D voxels; its chessboard distance k
 // (in cells) to the nearest cell with medium, found by breadth-first dilation, means every cell within k - 1 is
-// vacuum too, so a ray anywhere in the cell may advance 0.999 (k - 1) cell edges in ANY direction without leaving
-// vacuum.  The distance is stored in the bound grid itself as a NEGATIVE max (-jump, world units): the segment
+// vacuum too, so a ray anywhere in the cell may advance 0.999 (k - 1 - margin) cell edges in ANY direction without
+// leaving vacuum (see k_vac_encode for the margin).  The distance is stored in the bound grid itself as a NEGATIVE max (-jump, world units): the segment
 // loop of the fast renderer reads it with the load it does anyway.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_vac_init(const float2* __restrict__ bounds, uint8_t* __restrict__ d, size_t total)
@@ -404,24 +404,28 @@ __global__ void __launch_bounds__(256) k_vac_iter(uint8_t* __restrict__ d, int n
         if (hit) d[idx] = (uint8_t)k;
     }
 }
+// margin: cells with no medium in their own +-D window but closer than `margin` cells to one that has are FRINGE:
+// the window (D voxels) plus the trilinear footprint (1 voxel) need not cover a whole 0.05 segment, so such a segment
+// can still touch interpolated density.  They get the tiny positive max 1e-30 and are tracked exactly like the reference
+// tracks them (d_max floored to 1e-4, K.cu:1657-1658); only cells beyond the margin are skippable vacuum.
 __global__ void __launch_bounds__(256) k_vac_encode(float2* __restrict__ bounds, const uint8_t* __restrict__ d, size_t total, int kmax,
-                                                     float cell_world)
+                                                     int margin, float cell_world)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     {
         int k = d[i];
         if (k == 0) continue;
         if (k == 255) k = kmax + 1;  // nothing within kmax cells
-        bounds[i].x = -(0.999f * (float)(k - 1) * cell_world);
+        bounds[i].x = k <= margin ? 1e-30f : -(0.999f * (float)(k - 1 - margin) * cell_world);
     }
 }
-cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, float cell_world,
-                                cudaStream_t stream)
+cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, int margin,
+                                float cell_world, cudaStream_t stream)
 {
     size_t total = (size_t)ncx * ncy * ncz;
     k_vac_init<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, tmp, total);
     for (int k = 1; k <= kmax; k++) k_vac_iter<<<grid_for(total, 256, (size_t)148 * 32), 256, 0, stream>>>(tmp, ncx, ncy, ncz, k);
-    k_vac_encode<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, tmp, total, kmax, cell_world);
+    k_vac_encode<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, tmp, total, kmax, margin, cell_world);
     return cudaGetLastError();
 }
 

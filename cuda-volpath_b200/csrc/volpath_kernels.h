@@ -41,8 +41,8 @@ cudaError_t launch_fill_octets(const float* dense, int nx, int ny, int nz, int n
                                uint32_t n_slots, void* pool, int voxel_type, cudaStream_t stream);
 cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick, uint32_t n_slots, float* opacity_bricks,
                                       float3 light_dir, cudaStream_t stream);
-cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, float cell_world,
-                                cudaStream_t stream);
+cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, int margin,
+                                float cell_world, cudaStream_t stream);
 cudaError_t launch_sun_clear(const Scene& S, float3 sun, float step, float* out, cudaStream_t stream);
 cudaError_t launch_gather_opacity(const Scene& S, float* dense_out, cudaStream_t stream);
 

@@ -10,6 +10,21 @@ from test_gpu_parity import _ref_cuda, match_fraction, small_cloud
 pytestmark = pytest.mark.gpu
 
 
+def assert_same_in_the_mean(R, vp, P, spp, what, first=0):
+    """fast vs parity means, judged against the noise of the statistic itself: two independent parity renders (disjoint
+    frame ranges) give the Monte-Carlo scatter of the mean at this spp; fast must sit within 3 of those + 0.3 %."""
+    a = R.render(P, first, spp, mode=vp.MODE_PARITY)
+    b = R.render(P, first + spp, spp, mode=vp.MODE_PARITY)
+    f = R.render(P, first, spp, mode=vp.MODE_FAST)
+    assert np.isfinite(f).all()
+    for name, sl in (("radiance", np.s_[..., :3]), ("scatters", np.s_[..., 3])):
+        ma, mb, mf = a[sl].mean(), b[sl].mean(), f[sl].mean()
+        ref = 0.5 * (ma + mb)
+        noise = abs(ma - mb)
+        assert abs(mf - ref) <= 3.0 * noise + 0.003 * ref, (what, name, ma, mb, mf)
+    return a, f
+
+
 @pytest.fixture(scope="module")
 def R(vp):
     r = vp.Renderer(0)
@@ -37,10 +52,7 @@ def test_custom_box_with_anisotropic_voxels_vs_reference_kernel(R, oracle, vp):
     assert want[..., 3].sum() > 0
     assert match_fraction(got, want, 1e-5) >= 0.98
     # and the production renderer agrees in the mean on the same box
-    a = R.render(P, 0, 256, mode=vp.MODE_PARITY)
-    f = R.render(P, 0, 256, mode=vp.MODE_FAST)
-    assert abs(f[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
-    assert abs(f[..., 3].mean() - a[..., 3].mean()) <= 0.015 * a[..., 3].mean()
+    assert_same_in_the_mean(R, vp, P, 512, "custom box")
 
 
 @pytest.mark.parametrize("dims", [(1, 1, 1), (2, 3, 1), (9, 1, 17)])
@@ -82,10 +94,8 @@ def test_zero_albedo_and_the_scatter_cap(R, oracle, vp):
     got = R.render(P, 0, 2, mode=vp.MODE_PARITY)
     assert want[..., 3].max() <= 2 * 800 and (want[..., 3] >= 800).any()
     assert np.array_equal(got[..., 3] >= 800, want[..., 3] >= 800) or match_fraction(got, want, 1e-4) >= 0.9
-    f = R.render(P, 0, 32, mode=vp.MODE_FAST)
-    a = R.render(P, 0, 32, mode=vp.MODE_PARITY)
-    assert f[..., 3].max() <= 32 * 800
-    assert abs(f[..., 3].mean() - a[..., 3].mean()) <= 0.03 * a[..., 3].mean()
+    a, f = assert_same_in_the_mean(R, vp, P, 128, "scatter cap")
+    assert f[..., 3].max() <= 128 * 800 and (f[..., 3] >= 800).any()
 
 
 @pytest.mark.parametrize("store", ["u8", "f16", "f32"])
@@ -98,10 +108,7 @@ def test_fast_renderer_on_every_storage_type(R, oracle, vp, store):
     setup_renderer(R, vp, v, quant, True, env=env, **kw)
     P = vp.default_param(96, 64)
     P.density = 300.0
-    a = R.render(P, 0, 192, mode=vp.MODE_PARITY)
-    f = R.render(P, 0, 192, mode=vp.MODE_FAST)
-    assert abs(f[..., :3].mean() - a[..., :3].mean()) <= 0.01 * a[..., :3].mean()
-    assert abs(f[..., 3].mean() - a[..., 3].mean()) <= 0.015 * a[..., 3].mean()
+    assert_same_in_the_mean(R, vp, P, 512, "store " + store)
 
 
 @pytest.mark.parametrize("size", [(1, 1), (7, 3), (33, 5), (8, 4)])

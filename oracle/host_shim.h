@@ -80,6 +80,12 @@ inline cudaError_t memcpy2DToArray(cudaArray_t dst, size_t, size_t, const void* 
         memcpy(&A->bytes[(j * A->w) * ts], (const char*)src + j * spitch, width_bytes);
     return cudaSuccess;
 }
+inline cudaError_t memcpyToArray(cudaArray_t dst, size_t, size_t, const void* src, size_t bytes, cudaMemcpyKind)
+{
+    auto* A = reinterpret_cast<texemu::Array*>(dst);
+    memcpy(A->bytes.data(), src, bytes);
+    return cudaSuccess;
+}
 inline cudaError_t createTextureObject(cudaTextureObject_t* t, const cudaResourceDesc* r,
                                        const cudaTextureDesc* d, const void*)
 {
@@ -148,6 +154,7 @@ Launcher<K> make_launcher(K k, dim3 g, dim3 b)
 #define cudaMemcpy3D vps::memcpy3D
 #define cudaMemcpy2DToArrayAsync vps::memcpy2DToArray
 #define cudaMemcpy2DToArray vps::memcpy2DToArray
+#define cudaMemcpyToArray vps::memcpyToArray
 #define cudaCreateTextureObject vps::createTextureObject
 #define cudaCreateSurfaceObject vps::createSurfaceObject
 #define cudaDestroyTextureObject vps::destroyObject

@@ -48,6 +48,7 @@ inline V3    operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 inline V3    operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
 inline V3    operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 inline V3    operator/(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+inline V3    operator/(V3 a, float b) { return v3(a.x / b, a.y / b, a.z / b); }  // helper_math.h:997-1000
 inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline V3    cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 inline float host_rsqrtf(float x) { return 1.0f / sqrtf(x); }
@@ -262,6 +263,10 @@ struct Ctx
     texemu::Array  opacity;             // K.cu:540
     bool           have_opacity = false;
     texemu::Array  env;                 // K.cu:1098-1141
+    // env-map importance sampling (PASSIVE_ENVMAP 0 variant, K.cu:21, 904-1034, 1144-1210)
+    bool               passive_envmap = true;
+    std::vector<float> env_cdf_y, env_cdf_x;   // EnvmapCdfY / EnvmapCdfX textures (point, unnormalised coords)
+    float              env_pdfnorm_alt = 0.0f; // HDRpdfnormAlt
     float          inv_view[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // K.cu:626
     V3             sun_dir{0, 1, 0}, sun_power{0, 0, 0}, sun_power_original{0, 0, 0};  // K.cu:1254-1256
 
@@ -400,6 +405,98 @@ inline V3 background(const Ctx& c, V3 dir, int depth)
     return eval_envmap(c, dir);
 }
 
+// luminance (K.cu:946-954): float * double literals, summed in double, returned as float
+inline float luminance(V3 c) { return (float)(c.x * 0.2126 + c.y * 0.7152 + c.z * 0.0722); }
+
+// build_cdf_1d / build_cdf_2d + the host part of init_envmap (K.cu:1036-1070, 1144-1210), PRE_WARP 1, MULT_PDF 0
+inline float build_cdf_1d(const float* f, float* pdf, float* cdf, int size)
+{
+    if (size < 1) return 0;
+    float sum = 0.0f;
+    for (int i = 0; i < size; i++) sum += f[i];
+    float norm = 1.0f / sum;
+    float I    = 0.0f;
+    for (int i = 0; i < size; i++)
+    {
+        float p = f[i] * norm;
+        I += p;
+        pdf[i] = p;
+        cdf[i] = I;
+    }
+    cdf[size - 1] = 1.0f;
+    return sum;
+}
+inline void build_env_cdf(Ctx& c)
+{
+    const int w = c.env.w, h = c.env.h;
+    if (w < 1 || h < 1) return;
+    size_t             total = (size_t)w * h;
+    std::vector<float> lum(total);
+    for (size_t i = 0; i < total; i++)
+    {
+        float px[4];
+        memcpy(px, &c.env.bytes[i * 16], 16);
+        lum[i] = (float)(px[0] * 0.2126 + px[1] * 0.7152 + px[2] * 0.0722);  // luminance(float4)
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+        {
+            float phi = kPi * (y + 0.5f) / h;  // K.cu:1158
+            lum[x + (size_t)y * w] *= sinf(phi);
+        }
+    float lumsum = 0.0f;
+    for (size_t i = 0; i < total; i++) lumsum += lum[i];
+    const float k1TwoPiPi = 1.0f / kPi / kTwoPi;  // vecmath.h:16
+    c.env_pdfnorm_alt     = (float)w * (float)h * k1TwoPiPi / lumsum;
+    std::vector<float> pdfY(h), pdfX(total), row_sum(h);
+    c.env_cdf_y.assign(h, 0.0f);
+    c.env_cdf_x.assign(total, 0.0f);
+    for (int y = 0; y < h; y++)
+        row_sum[y] = build_cdf_1d(lum.data() + (size_t)y * w, pdfX.data() + (size_t)y * w, c.env_cdf_x.data() + (size_t)y * w, w);
+    build_cdf_1d(row_sum.data(), pdfY.data(), c.env_cdf_y.data(), h);
+}
+
+// sample_y / sample_x (K.cu:904-944): lower-bound binary searches in the CDF rows
+inline int env_sample_y(const Ctx& c, float r)
+{
+    int begin = 0, end = c.env.h - 1;
+    while (end > begin)
+    {
+        int mid = begin + (end - begin) / 2;
+        if (c.env_cdf_y[mid] >= r) end = mid; else begin = mid + 1;
+    }
+    return begin;
+}
+inline int env_sample_x(const Ctx& c, int y, float r)
+{
+    int begin = 0, end = c.env.w - 1;
+    while (end > begin)
+    {
+        int mid = begin + (end - begin) / 2;
+        if (c.env_cdf_x[(size_t)y * c.env.w + mid] >= r) end = mid; else begin = mid + 1;
+    }
+    return begin;
+}
+// sample_envmap (K.cu:979-1009): u, v in: random numbers; out: texel-centre coordinates; returns the pdf
+inline float sample_envmap(const Ctx& c, float& u, float& v, V3& col)
+{
+    int iy = env_sample_y(c, v);
+    int ix = env_sample_x(c, iy, u);
+    u      = ((float)ix + 0.5f) / (float)c.env.w;
+    v      = ((float)iy + 0.5f) / (float)c.env.h;
+    texemu::Texture t = c.tex_env();
+    col    = v3(texemu::fetch2(t, u, v, 0), texemu::fetch2(t, u, v, 1), texemu::fetch2(t, u, v, 2));
+    return luminance(col) * c.env_pdfnorm_alt;
+}
+inline float pdf_envmap(const Ctx& c, V3 col) { return luminance(col) * c.env_pdfnorm_alt; }  // K.cu:1011-1034
+inline V3 uv_to_dir(float u, float v)  // K.cu:897-902
+{
+    float theta = u * kTwoPi;
+    float phi   = v * kPi;
+    return v3(sinf(phi) * sinf(theta), cosf(phi), sinf(phi) * -cosf(theta));
+}
+inline float mis_balance(float a, float b) { return a / (a + b); }  // K.cu:54
+
 // Tr_spectral (K.cu:754-808)
 inline V3 tr_spectral(const Ctx& c, V3 start, V3 end, float inv_sigma, float density, V3 sigma_t, RefRng& rng,
                       uint64_t* n_fetch)
@@ -470,7 +567,8 @@ inline void trace_path(const Ctx& c, const Param& P, uint32_t x, uint32_t y, int
         bool use_decomposition = d_min > 0.0f;                                      // K.cu:2021
         if (!hit)
         {
-            radiance = radiance + background(c, d, num_scatters) * throughput;      // K.cu:2027 (PASSIVE_ENVMAP)
+            // K.cu:2026-2030: passive env map adds the environment at any depth, the MIS variant only at depth 0
+            if (c.passive_envmap || num_scatters == 0) radiance = radiance + background(c, d, num_scatters) * throughput;
             if (st) st->env_eval++;
             break;
         }
@@ -575,6 +673,39 @@ inline void trace_path(const Ctx& c, const Param& P, uint32_t x, uint32_t y, int
                                 st ? &st->shadow_fetch : nullptr);
             }
             radiance = radiance + c.sun_power * (throughput * ph * a);  // K.cu:2188-2189, 2209-2210
+
+            if (!c.passive_envmap)
+            {
+                // one-sample MIS between phase-function and env-map sampling (K.cu:2220-2297)
+                const float P_phase = 0.5f, P_envmap = 1.0f - P_phase;
+                if (rng.next() < P_phase)
+                {
+                    float u = rng.next();
+                    float v = rng.next();
+                    V3    brdf_dir = frame.to_world(phase.sample_local(u, v));
+                    V3    envc     = eval_envmap(c, brdf_dir);
+                    float pdf_brdf = phase.evaluate(dot(frame.n, brdf_dir));
+                    float pdf_env_virtual = pdf_envmap(c, envc);
+                    float weight   = mis_balance(pdf_brdf * P_phase, pdf_env_virtual * P_envmap) / P_phase;
+                    V3    a2 = tr_spectral(c, pos, brdf_dir * 1e10f, inv_sigma2, density_prime2, sigma_t_spectral, rng,
+                                           st ? &st->shadow_fetch : nullptr);
+                    radiance = radiance + envc * (throughput * weight * a2);
+                }
+                else
+                {
+                    float u = rng.next();
+                    float v = rng.next();
+                    V3    envc;
+                    float pdf_env = sample_envmap(c, u, v, envc);
+                    if (pdf_env <= 0.0f) continue;  // K.cu:2266: back to the while loop WITHOUT a new direction (quirk)
+                    V3    envmap_dir = uv_to_dir(u, v);
+                    float pdf_brdf_virtual = phase.evaluate(dot(frame.n, envmap_dir));
+                    float weight = mis_balance(pdf_env * P_envmap, pdf_brdf_virtual * P_phase) / P_envmap;
+                    V3    a2 = tr_spectral(c, pos, envmap_dir * 1e10f, inv_sigma2, density_prime2, sigma_t_spectral, rng,
+                                           st ? &st->shadow_fetch : nullptr);
+                    radiance = radiance + envc * (throughput * phase.evaluate(dot(frame.n, envmap_dir)) / pdf_env * weight * a2);
+                }
+            }
         }
         // K.cu:2301 -- device order: first draw -> rnd0 (cos theta), second -> rnd1 (phi)  (Q6)
         float r0 = rng.next();
@@ -778,6 +909,16 @@ int vo_set_envmap(void* h, const float* rgba, int w, int hh)  // init_envmap (K.
     Ctx& c = *(Ctx*)h;
     c.env.alloc(w, hh, 1, texemu::FMT_F32x4);
     memcpy(c.env.bytes.data(), rgba, (size_t)w * hh * 16);
+    if (!c.passive_envmap) build_env_cdf(c);
+    return 0;
+}
+
+// PASSIVE_ENVMAP switch (K.cu:21): 0 builds the CDF tables like init_envmap does and enables the MIS block
+int vo_set_env_sampling(void* h, int enable)
+{
+    Ctx& c           = *(Ctx*)h;
+    c.passive_envmap = enable == 0;
+    if (!c.passive_envmap) build_env_cdf(c);
     return 0;
 }
 

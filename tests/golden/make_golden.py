@@ -97,6 +97,19 @@ def main():
     Pj.density = 100.0
     out["param_julia"] = np.frombuffer(bytes(Pj), np.uint8).copy()
     out["render_julia_f0_2"] = rj.render(Pj, 0, 2)
+    # the PASSIVE_ENVMAP 0 build: env-map importance sampling + one-sample MIS (K.cu:904-1034, 2220-2297)
+    rm = RefHost(mis=True)
+    rs = np.random.RandomState(5)
+    env = (rs.rand(8, 16, 4).astype(np.float32) ** 3 * 4).astype(np.float32)
+    env[..., 3] = 1
+    env[6:, :, :3] = 0  # rows the CDF can never pick
+    out["mis_env"] = env
+    for name, par in (("gray", P), ("chroma", Pc)):
+        rm.set_volume(vol, False, None, linear=True)
+        rm.set_envmap(env)
+        rm.set_sun(np.array([0.0, 0.951057, -0.309017], np.float32), np.array([51797.3, 42480.1, 32578.5], np.float32))
+        rm.set_inv_view(vp.inv_view_matrix())
+        out["render_mis_" + name + "_f0_3"] = rm.render(par, 0, 3)
     np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), **out)
     print("wrote ref_golden.npz with", len(out), "arrays")
 

@@ -49,6 +49,7 @@ class Oracle:
         L.vo_set_filter.argtypes = [c_vp, ctypes.c_int]
         L.vo_set_envmap.argtypes = [c_vp, c_fp, ctypes.c_int, ctypes.c_int]
         L.vo_set_sun.argtypes = [c_vp, c_fp, c_fp]
+        L.vo_set_env_sampling.argtypes = [c_vp, ctypes.c_int]
         L.vo_set_inv_view.argtypes = [c_vp, c_fp]
         L.vo_precompute_opacity.argtypes = [c_vp, c_fp]
         L.vo_get_bounds.argtypes = [c_vp, c_vp]
@@ -101,6 +102,9 @@ class Oracle:
     def set_sun(self, sun_dir, sun_power):
         d, p = np.ascontiguousarray(sun_dir, np.float32), np.ascontiguousarray(sun_power, np.float32)
         self.L.vo_set_sun(self.h, _fp(d), _fp(p))
+
+    def set_env_sampling(self, enable):
+        self.L.vo_set_env_sampling(self.h, int(enable))
 
     def set_inv_view(self, m12):
         m = np.ascontiguousarray(m12, np.float32)
@@ -254,8 +258,8 @@ class _RefBase:
 
 
 class RefHost(_RefBase):
-    def __init__(self, instrumented=False, julia=False):
-        name = "libvolpath_ref_host%s%s.so" % ("_julia" if julia else "", "_instr" if instrumented else "")
+    def __init__(self, instrumented=False, julia=False, mis=False):
+        name = "libvolpath_ref_host%s%s%s.so" % ("_julia" if julia else "", "_mis" if mis else "", "_instr" if instrumented else "")
         self._bind(ctypes.CDLL(os.path.join(REF_DIR, name)))
 
     def render(self, param, first_frame, n_frames, accum=None):
@@ -268,8 +272,8 @@ class RefHost(_RefBase):
 class RefCuda(_RefBase):
     """The reference kernel rebuilt for sm_100 -- needs a GPU."""
 
-    def __init__(self, instrumented=False, julia=False):
-        name = "libvolpath_ref_cuda%s%s.so" % ("_julia" if julia else "", "_instr" if instrumented else "")
+    def __init__(self, instrumented=False, julia=False, mis=False):
+        name = "libvolpath_ref_cuda%s%s%s.so" % ("_julia" if julia else "", "_mis" if mis else "", "_instr" if instrumented else "")
         L = ctypes.CDLL(os.path.join(REF_DIR, name))
         self._bind(L)
         L.ref_dev_alloc.restype = c_vp

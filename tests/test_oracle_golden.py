@@ -111,3 +111,22 @@ def test_resolve_kernels(oracle):
     dst = np.empty_like(src)
     oracle.L.vo_scale(dst.ctypes.data_as(oracle.L.vo_scale.argtypes[0]), src.ctypes.data_as(oracle.L.vo_scale.argtypes[1]), 37, 0.25)
     assert np.array_equal(dst, src * np.float32(0.25))
+
+
+@pytest.mark.parametrize("name,pkey", [("gray", "param_default"), ("chroma", "param_chroma")])
+def test_env_importance_sampling_mis_variant_bit_for_bit(golden, vp, name, pkey):
+    """PASSIVE_ENVMAP 0 (compiled out in the reference as shipped, K.cu:21): CDF tables built like init_envmap does
+    (K.cu:1144-1210), lower-bound sampling, one-sample MIS between phase and env-map sampling (K.cu:2220-2297)."""
+    from oraclelib import Oracle
+
+    o = Oracle()
+    o.set_env_sampling(True)
+    setup_scene(o, vp, golden["vol_f32"], False, True, env=golden["mis_env"])
+    P = param_from_bytes(vp, golden[pkey])
+    got = o.render(P, 0, 3)
+    want = golden["render_mis_" + name + "_f0_3"]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # and it is a different estimator of the same image: the passive variant differs per sample
+    o.set_env_sampling(False)
+    assert not np.array_equal(o.render(P, 0, 3), want)
+    o.close()

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "volpath_common.cuh"
 #include "volpath_kernels.h"
@@ -61,6 +62,10 @@ struct vp_context
     float*    opacity     = nullptr;
     float*    sun_clear   = nullptr;
     float4*   env         = nullptr;
+    std::vector<float> env_host;      // host copy of the env map (the CDF tables are built on the host, like init_envmap)
+    float*    env_cdf_y   = nullptr;
+    float*    env_cdf_x   = nullptr;
+    bool      env_sampling = false;   // the reference's PASSIVE_ENVMAP 0 variant
     float4*   host_acc    = nullptr;  // device accumulator of vp_render_to_host
     size_t    host_acc_bytes = 0;
     uint32_t  n_slots     = 0;
@@ -135,6 +140,61 @@ static void set_box(vp_context* c, int nx, int ny, int nz, const float* bmin, co
     S.vs_scale = make_float3(S.l_inv.x * nx, S.l_inv.y * ny, S.l_inv.z * nz);
     S.vs_off   = make_float3(-S.bmin.x * S.vs_scale.x, -S.bmin.y * S.vs_scale.y, -S.bmin.z * S.vs_scale.z);
     S.vs_off_lin = make_float3(S.vs_off.x - 0.5f, S.vs_off.y - 0.5f, S.vs_off.z - 0.5f);
+}
+
+// host part of init_envmap for the PASSIVE_ENVMAP 0 variant (K.cu:1036-1070, 1144-1210; PRE_WARP 1): luminance * sin(phi),
+// row CDFs + the CDF of the row sums, HDRpdfnormAlt.  Same float sequence as the reference's host code.
+static float build_cdf_1d(const float* f, float* cdf, int size)
+{
+    float sum = 0.0f;
+    for (int i = 0; i < size; i++) sum += f[i];
+    float norm = 1.0f / sum;
+    float I    = 0.0f;
+    for (int i = 0; i < size; i++)
+    {
+        float p = f[i] * norm;
+        I += p;
+        cdf[i] = I;
+    }
+    cdf[size - 1] = 1.0f;
+    return sum;
+}
+static int update_env_sampling(vp_context* c)
+{
+    Scene& S  = c->S;
+    S.env_mis = 0;
+    if (!c->env_sampling) return VP_OK;
+    const int w = S.env_w, h = S.env_h;
+    if (c->env_host.size() != (size_t)w * h * 4) return fail(VP_ERR_INVALID, "env sampling needs an environment map (init_envmap)");
+    const size_t       total = (size_t)w * h;
+    std::vector<float> lum(total), cdf_x(total), cdf_y(h), row_sum(h);
+    for (size_t i = 0; i < total; i++)
+    {
+        const float* px = &c->env_host[i * 4];
+        lum[i]          = (float)(px[0] * 0.2126 + px[1] * 0.7152 + px[2] * 0.0722);  // luminance(float4), K.cu:946
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+        {
+            float phi = kPi * (y + 0.5f) / h;  // K.cu:1158
+            lum[x + (size_t)y * w] *= sinf(phi);
+        }
+    float lumsum = 0.0f;
+    for (size_t i = 0; i < total; i++) lumsum += lum[i];
+    const float k1TwoPiPi = 1.0f / kPi / kTwoPi;  // vecmath.h:16
+    S.env_pdfnorm_alt     = (float)w * (float)h * k1TwoPiPi / lumsum;
+    for (int y = 0; y < h; y++) row_sum[y] = build_cdf_1d(lum.data() + (size_t)y * w, cdf_x.data() + (size_t)y * w, w);
+    build_cdf_1d(row_sum.data(), cdf_y.data(), h);
+    dev_free(c->env_cdf_x);
+    dev_free(c->env_cdf_y);
+    VP_CUDA(cudaMalloc(&c->env_cdf_x, total * sizeof(float)));
+    VP_CUDA(cudaMalloc(&c->env_cdf_y, (size_t)h * sizeof(float)));
+    VP_CUDA(cudaMemcpy(c->env_cdf_x, cdf_x.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    VP_CUDA(cudaMemcpy(c->env_cdf_y, cdf_y.data(), (size_t)h * sizeof(float), cudaMemcpyHostToDevice));
+    S.env_cdf_x = c->env_cdf_x;
+    S.env_cdf_y = c->env_cdf_y;
+    S.env_mis   = 1;
+    return VP_OK;
 }
 
 // (re)build the sun-clear distances of the fast renderer: needs the bound grid and the sun direction
@@ -322,6 +382,8 @@ int vp_destroy(vp_context* c)
     cudaSetDevice(c->device);
     free_volume(c);
     dev_free(c->env);
+    dev_free(c->env_cdf_x);
+    dev_free(c->env_cdf_y);
     dev_free(c->d_stats);
     dev_free(c->d_work);
     dev_free(c->host_acc);
@@ -422,7 +484,21 @@ int vp_set_envmap(vp_context* c, const float* rgba, int width, int height)
     VP_CUDA(cudaMalloc(&c->env, (size_t)width * height * sizeof(float4)));
     VP_CUDA(cudaMemcpy(c->env, rgba, (size_t)width * height * sizeof(float4), cudaMemcpyHostToDevice));
     c->S.env = c->env; c->S.env_w = width; c->S.env_h = height;
-    return VP_OK;
+    c->env_host.assign(rgba, rgba + (size_t)width * height * 4);
+    return update_env_sampling(c);
+}
+
+int vp_set_env_sampling(vp_context* c, int enable)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    VP_CUDA(cudaSetDevice(c->device));
+    c->env_sampling = enable != 0;
+    if (!c->env_sampling)
+    {
+        c->S.env_mis = 0;
+        return VP_OK;
+    }
+    return update_env_sampling(c);
 }
 
 int vp_set_sun(vp_context* c, const float* dir3, const float* power3)
@@ -482,6 +558,7 @@ int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int fra
     }
     else if (mode == VP_MODE_FAST || mode == VP_MODE_WAVE)
     {
+        if (c->S.env_mis && mode == VP_MODE_WAVE) return fail(VP_ERR_UNSUPPORTED, "vp_render: env-map sampling is not implemented in the wavefront form");
         if (!c->S.julia && !c->S.bounds_cell) return fail(VP_ERR_INVALID, "vp_render: fast mode needs VP_BOUNDS_CELL");
         // all frames of the call are ONE launch (one work pool), as long as tiles * frames fits 31 bits
         const long long tiles = (long long)((p->width + 7) / 8) * ((p->height + 3) / 4);

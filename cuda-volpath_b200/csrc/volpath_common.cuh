@@ -49,6 +49,11 @@ struct Scene
     const float*    opacity;       // per brick slot: 9^3 floats (+pad)
     const float4*   env;           // [env_h][env_w]
     int             env_w, env_h;
+    // env-map importance sampling (the reference's PASSIVE_ENVMAP 0 variant, K.cu:21): CDF rows + normalisation
+    int             env_mis;
+    const float*    env_cdf_y;     // [env_h]          (EnvmapCdfY, K.cu:1174)
+    const float*    env_cdf_x;     // [env_h][env_w]   (EnvmapCdfX, K.cu:1192)
+    float           env_pdfnorm_alt;  // HDRpdfnormAlt (K.cu:1166)
     float3          sun_dir, sun_power, sun_power_original;  // K.cu:1254-1256
     float           inv_view[12];                            // K.cu:626
     // fast renderer: world -> voxel space (p * N) as one FMA per axis
@@ -337,6 +342,38 @@ __device__ __forceinline__ float3 eval_envmap(const Scene& S, float3 dir)
     float4 c = __ldg(S.env + (size_t)j * S.env_w + i);
     return f3(c.x, c.y, c.z);
 }
+// env-map importance sampling (K.cu:904-1034, MULT_PDF 0, PRE_WARP 1)
+__device__ __forceinline__ float env_luminance(float3 c) { return (float)(c.x * 0.2126 + c.y * 0.7152 + c.z * 0.0722); }  // K.cu:951
+__device__ __forceinline__ int env_sample_row(const float* __restrict__ cdf, int n, float r)  // sample_y / sample_x
+{
+    int begin = 0, end = n - 1;
+    while (end > begin)
+    {
+        int mid = begin + (end - begin) / 2;
+        if (__ldg(cdf + mid) >= r) end = mid; else begin = mid + 1;
+    }
+    return begin;
+}
+__device__ __forceinline__ float sample_envmap(const Scene& S, float& u, float& v, float3& col)  // K.cu:979-1009
+{
+    int iy = env_sample_row(S.env_cdf_y, S.env_h, v);
+    int ix = env_sample_row(S.env_cdf_x + (size_t)iy * S.env_w, S.env_w, u);
+    u      = ((float)ix + 0.5f) / (float)S.env_w;
+    v      = ((float)iy + 0.5f) / (float)S.env_h;
+    int    i = clampi((int)floorf(__fmul_rn(u, (float)S.env_w)), 0, S.env_w - 1);
+    int    j = clampi((int)floorf(__fmul_rn(v, (float)S.env_h)), 0, S.env_h - 1);
+    float4 c = __ldg(S.env + (size_t)j * S.env_w + i);
+    col      = f3(c.x, c.y, c.z);
+    return env_luminance(col) * S.env_pdfnorm_alt;
+}
+__device__ __forceinline__ float pdf_envmap(const Scene& S, float3 col) { return env_luminance(col) * S.env_pdfnorm_alt; }  // K.cu:1011
+__device__ __forceinline__ float3 uv_to_dir(float u, float v)  // K.cu:897-902
+{
+    float theta = u * kTwoPi;
+    float phi   = v * kPi;
+    return f3(sinf(phi) * sinf(theta), cosf(phi), sinf(phi) * -cosf(theta));
+}
+
 __device__ __forceinline__ float3 background(const Scene& S, float3 dir, int depth)
 {
     if (depth == 0 && (dot3(dir, S.sun_dir) > 94.0f / sqrtf(94.0f * 94.0f + 0.45f * 0.45f))) return S.sun_power_original;

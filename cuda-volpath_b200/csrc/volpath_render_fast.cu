@@ -64,6 +64,10 @@ enum : uint32_t
     kNeedRay   = 32,   // (o, s) changed: intersect the box before the next segment
     kKillX = 64, kKillY = 128, kKillZ = 256,
     kEscaped   = 512,  // path left the medium: environment lookup + accumulate pending (done in the path block)
+    // env-map importance sampling variant (MIS = true) only: the scatter block runs in three stages
+    kMisWalk   = 1024,  // the shadow walk in progress is the one toward the MIS direction (else: toward the sun)
+    kScatB     = 2048,  // sun NEE done: choose the MIS direction and start its shadow walk
+    kScatC     = 4096,  // both NEE walks done: sample the scattered direction
 };
 
 struct Philox
@@ -157,8 +161,8 @@ __device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t 
     atomicAdd(d_sum + pix, v);
 }
 
-template <int VT, bool JULIA, bool GRAY, bool STATS>
-__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
+template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS>
+__global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
                                                                   unsigned long long* __restrict__ d_work,
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
     unsigned long long w_next = 0, w_end = 0;
     // lane state
     float3   o = f3(0.f), s = f3(0.f), pend = f3(0.f), T = f3(1.f), L = f3(0.f);
+    float3   C = f3(0.f);  // MIS only: radiance the pending env-direction walk will add if it survives
     float    dist = 0.f, lim = 0.f, inv = 0.f, dens = 0.f, maj = 0.f, sigc = 0.f, t_exit = 0.f, ph = 0.f, dmax = 0.f;
     int      n = 0;
     uint32_t st = kModePath, pix = 0;
@@ -225,7 +230,8 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
                     // finish the previous path here, where many lanes are in the same situation: environment /
                     // sun disk (acosf + atanf + one texel), then one vector atomic
                     if (STATS) c_env++;
-                    L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
+                    // K.cu:2026-2030: with env-map sampling the environment is picked up by escaping paths at depth 0 only
+                    if (!MIS || n == 0) L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
                     accumulate(d_sum, pix, L, n, P.brightness);
                     st = kModePath;
                 }
@@ -351,13 +357,30 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
                     if (past || (st & (kKillX | kKillY | kKillZ)) == (kKillX | kKillY | kKillZ))
                     {
                         float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
-                        L        = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
-                        s        = pend;
-                        st       = kModeSeg | kNeedRay;
-                        if (n >= kMaxDepth)
+                        if (MIS)
                         {
-                            accumulate(d_sum, pix, L, n, P.brightness);
-                            st = kModePath;
+                            // sun walk done -> MIS stage; MIS walk done -> direction sampling stage
+                            if (st & kMisWalk)
+                            {
+                                L  = L + C * a;
+                                st = kModeScat | kScatC;
+                            }
+                            else
+                            {
+                                L  = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
+                                st = kModeScat | kScatB;
+                            }
+                        }
+                        else
+                        {
+                            L  = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
+                            s  = pend;
+                            st = kModeSeg | kNeedRay;
+                            if (n >= kMaxDepth)
+                            {
+                                accumulate(d_sum, pix, L, n, P.brightness);
+                                st = kModePath;
+                            }
                         }
                     }
                 }
@@ -413,20 +436,86 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
         }
         else  // kModeScat
         {
-            if (mode == kModeScat)
+            if (mode == kModeScat && MIS && (st & (kScatB | kScatC)))
+            {
+                // ---- env-map sampling variant, stages B and C of a scattering event (incoming direction in pend) ----
+                float  sr_pre = fmaxf(0.0f, fminf(1.0f, (n - 1 - 5) * 0.066666666666666666667f));
+                float  g      = (1 - sr_pre) * P.g;
+                float3 ft, fb;
+                make_frame(pend, ft, fb);
+                if (st & kScatB)
+                {
+                    // one-sample MIS between phase-function and env-map sampling (K.cu:2220-2297)
+                    float rsel, u, v, unused;
+                    rng.draw(rsel, u);
+                    rng.draw(v, unused);
+                    float3 dir, envc;
+                    bool   ok = true;
+                    if (rsel < 0.5f)
+                    {
+                        float3 ls = hg_sample_local_fast(g, u, v);
+                        dir       = ft * ls.x + fb * ls.y + pend * ls.z;
+                        envc      = eval_envmap(S, dir);
+                        float pdf_brdf = hg_eval_fast(g, dot3(pend, dir));
+                        float pdf_env  = pdf_envmap(S, envc);
+                        float weight   = __fdividef(pdf_brdf * 0.5f, pdf_brdf * 0.5f + pdf_env * 0.5f) * 2.0f;
+                        C              = envc * ((GRAY ? f3(T.x) : T) * weight);
+                    }
+                    else
+                    {
+                        float pdf_env = sample_envmap(S, u, v, envc);
+                        ok            = pdf_env > 0.0f;  // (the reference `continue`s here, K.cu:2266: probability ~2^-23)
+                        dir           = uv_to_dir(u, v);
+                        float pb      = hg_eval_fast(g, dot3(pend, dir));
+                        float weight  = __fdividef(pdf_env * 0.5f, pdf_env * 0.5f + pb * 0.5f) * 2.0f;
+                        C             = envc * ((GRAY ? f3(T.x) : T) * (__fdividef(pb, pdf_env) * weight));
+                    }
+                    if (ok)
+                    {
+                        s = normalize3(dir);
+                        float tn, tf;
+                        box_slabs_fast(S, o, s, tn, tf);
+                        dist = 0.0f;
+                        lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
+                        inv  = __fdividef(1.0f, max_sig_t * dens * dmax);
+                        st   = kModeStep | kShadow | kMisWalk;
+                    }
+                    else
+                        st = kModeScat | kScatC;
+                }
+                else
+                {
+                    float r0, r1;
+                    rng.draw(r0, r1);
+                    float3 l = hg_sample_local_fast(g, r0, r1);
+                    s        = normalize3(ft * l.x + fb * l.y + pend * l.z);
+                    st       = kModeSeg | kNeedRay;
+                    if (n >= kMaxDepth)
+                    {
+                        accumulate(d_sum, pix, L, n, P.brightness);
+                        st = kModePath;
+                    }
+                }
+            }
+            else if (mode == kModeScat)
             {
                 // ---- scattering event at o, incoming direction s ----
                 if (STATS) c_scat++;
                 float sr_pre = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                 float g      = (1 - sr_pre) * P.g;  // Q4: g of the pre-increment count
                 n++;
-                float3 ft, fb;
-                make_frame(s, ft, fb);
                 ph = hg_eval_fast(g, dot3(s, S.sun_dir));
-                float r0, r1;
-                rng.draw(r0, r1);
-                float3 l = hg_sample_local_fast(g, r0, r1);
-                pend     = normalize3(ft * l.x + fb * l.y + s * l.z);
+                if (MIS)
+                    pend = s;  // keep the incoming direction: the new one is sampled after both NEE walks (stage C)
+                else
+                {
+                    float3 ft, fb;
+                    make_frame(s, ft, fb);
+                    float r0, r1;
+                    rng.draw(r0, r1);
+                    float3 l = hg_sample_local_fast(g, r0, r1);
+                    pend     = normalize3(ft * l.x + fb * l.y + s * l.z);
+                }
                 float sr = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                 dens     = ((1 - sr) + sr * (1 - P.g)) * P.density;
                 if ((int)rng.frame > 10 && n > 20)  // K.cu:2183: precomputed sun opacity
@@ -435,12 +524,17 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
                     float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, o, false) : 0.0f;
                     float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
                     L          = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
-                    s          = pend;
-                    st         = kModeSeg | kNeedRay;
-                    if (n >= kMaxDepth)
+                    if (MIS)
+                        st = kModeScat | kScatB;
+                    else
                     {
-                        accumulate(d_sum, pix, L, n, P.brightness);
-                        st = kModePath;
+                        s  = pend;
+                        st = kModeSeg | kNeedRay;
+                        if (n >= kMaxDepth)
+                        {
+                            accumulate(d_sum, pix, L, n, P.brightness);
+                            st = kModePath;
+                        }
                     }
                 }
                 else
@@ -473,7 +567,7 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) k_render_fast(co
     }
 }
 
-template <int VT, bool JULIA, bool GRAY>
+template <int VT, bool JULIA, bool GRAY, bool MIS>
 static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
                                  unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
@@ -483,12 +577,12 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
     unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
     unsigned long long want  = (items + kClaim - 1) / kClaim;                    // warps that can get a claim
     unsigned long long ctas  = (want + kFastThreads / 32 - 1) / (kFastThreads / 32);
-    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * kFastCtasPerSm ? ctas : (unsigned long long)num_sms * kFastCtasPerSm);
+    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * (MIS ? 8 : kFastCtasPerSm) ? ctas : (unsigned long long)num_sms * (MIS ? 8 : kFastCtasPerSm));
     if (grid < 1) grid = 1;
     if (d_stats)
-        k_render_fast<VT, JULIA, GRAY, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
+        k_render_fast<VT, JULIA, GRAY, MIS, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
     else
-        k_render_fast<VT, JULIA, GRAY, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
+        k_render_fast<VT, JULIA, GRAY, MIS, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
     return cudaGetLastError();
 }
 
@@ -496,9 +590,14 @@ cudaError_t launch_render_fast(const Scene& S, float4* d_sum, int first_frame, i
                                unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
     const bool gray = P.sigma_t.x == P.sigma_t.y && P.sigma_t.y == P.sigma_t.z && P.albedo.x == P.albedo.y && P.albedo.y == P.albedo.z;
-#define VP_FAST(VT, J)                                                                                                          \
-    return gray ? launch_fast_t<VT, J, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream) \
-                : launch_fast_t<VT, J, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)
+#define VP_FAST(VT, J)                                                                                                                  \
+    do {                                                                                                                                \
+        if (S.env_mis)                                                                                                                  \
+            return gray ? launch_fast_t<VT, J, true, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream) \
+                        : launch_fast_t<VT, J, false, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream); \
+        return gray ? launch_fast_t<VT, J, true, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)     \
+                    : launch_fast_t<VT, J, false, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);   \
+    } while (0)
     if (S.julia) VP_FAST(kF32, true);
     if (S.voxel_type == kU8) VP_FAST(kU8, false);
     if (S.voxel_type == kF16) VP_FAST(kF16, false);

@@ -63,7 +63,7 @@ __device__ float3 tr_spectral(const Scene& S, float3 start, float3 end, float in
     return f3((float)(1 - xterm), (float)(1 - yterm), (float)(1 - zterm));
 }
 
-template <class M>
+template <class M, bool MIS>
 __device__ float4 trace_path_parity(const Scene& S, const vp_param& P, uint32_t x, uint32_t y, int spp)
 {
     const float density = P.density;
@@ -96,7 +96,8 @@ __device__ float4 trace_path_parity(const Scene& S, const vp_param& P, uint32_t 
         bool   use_decomposition = d_min > 0.0f;
         if (!hit)
         {
-            radiance = radiance + background(S, d, num_scatters) * throughput;
+            // K.cu:2026-2030: the MIS variant adds the environment only at depth 0
+            if (!MIS || num_scatters == 0) radiance = radiance + background(S, d, num_scatters) * throughput;
             break;
         }
         float3 pos  = o + d * t_near;
@@ -189,6 +190,40 @@ __device__ float4 trace_path_parity(const Scene& S, const vp_param& P, uint32_t 
                 a = tr_spectral<M>(S, pos, S.sun_dir * 1e10f, inv_sigma2, density_prime2, sigma_t_spectral, rng);
             }
             radiance = radiance + S.sun_power * (throughput * ph * a);
+
+            if (MIS)
+            {
+                // one-sample MIS between phase-function and env-map sampling (K.cu:2220-2297)
+                const float P_phase = 0.5f, P_envmap = 1.0f - P_phase;
+                if (rng.next() < P_phase)
+                {
+                    float  u = rng.next();
+                    float  v = rng.next();
+                    float3 ls = hg_sample_local(g, u, v);
+                    float3 brdf_dir = ft * ls.x + fb * ls.y + d * ls.z;
+                    float3 envc     = eval_envmap(S, brdf_dir);
+                    float  pdf_brdf = hg_evaluate(g, dot3(d, brdf_dir));
+                    float  pdf_env_virtual = pdf_envmap(S, envc);
+                    float  weight = (pdf_brdf * P_phase) / (pdf_brdf * P_phase + pdf_env_virtual * P_envmap) / P_phase;
+                    float3 a2 = tr_spectral<M>(S, pos, brdf_dir * 1e10f, inv_sigma2, density_prime2, sigma_t_spectral, rng);
+                    radiance  = radiance + envc * (throughput * weight * a2);
+                }
+                else
+                {
+                    float  u = rng.next();
+                    float  v = rng.next();
+                    float3 envc;
+                    float  pdf_env = sample_envmap(S, u, v, envc);
+                    if (pdf_env <= 0.0f) continue;  // K.cu:2266: no new direction, the ray restarts from its old origin
+                    float3 envmap_dir = uv_to_dir(u, v);
+                    float  pdf_brdf_virtual = hg_evaluate(g, dot3(d, envmap_dir));
+                    float  weight = (pdf_env * P_envmap) / (pdf_env * P_envmap + pdf_brdf_virtual * P_phase) / P_envmap;
+                    float3 a2 = tr_spectral<M>(S, pos, envmap_dir * 1e10f, inv_sigma2, density_prime2, sigma_t_spectral, rng);
+                    float3 tw = throughput * hg_evaluate(g, dot3(d, envmap_dir));
+                    tw        = f3(tw.x / pdf_env, tw.y / pdf_env, tw.z / pdf_env);
+                    radiance  = radiance + envc * (tw * weight * a2);
+                }
+            }
         }
         float  r0 = rng.next();  // device order: first draw -> cos(theta), second -> phi (Q6)
         float  r1 = rng.next();
@@ -201,7 +236,7 @@ __device__ float4 trace_path_parity(const Scene& S, const vp_param& P, uint32_t 
     return make_float4(fmaxf(radiance.x, 0.0f), fmaxf(radiance.y, 0.0f), fmaxf(radiance.z, 0.0f), (float)num_scatters);
 }
 
-template <int VT, bool JULIA>
+template <int VT, bool JULIA, bool MIS>
 __global__ void __launch_bounds__(64) k_render_parity(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                        int first_frame, int n_frames, int frame_stride,
                                                        const __grid_constant__ vp_param P)
@@ -212,7 +247,7 @@ __global__ void __launch_bounds__(64) k_render_parity(const __grid_constant__ Sc
     float4 v = d_sum[x + (size_t)y * P.width];
     for (int f = 0; f < n_frames; f++)
     {
-        float4 c = trace_path_parity<ParityMedium<VT, JULIA>>(S, P, x, y, first_frame + f * frame_stride);
+        float4 c = trace_path_parity<ParityMedium<VT, JULIA>, MIS>(S, P, x, y, first_frame + f * frame_stride);
         v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;  // K.cu:2315
     }
     d_sum[x + (size_t)y * P.width] = v;
@@ -223,14 +258,22 @@ cudaError_t launch_render_parity(const Scene& S, float4* d_sum, int first_frame,
 {
     dim3 block(8, 8);  // H.cpp:100
     dim3 grid((P.width + block.x - 1) / block.x, (P.height + block.y - 1) / block.y);
+#define VP_PARITY(VT, J)                                                                                        \
+    do {                                                                                                        \
+        if (S.env_mis)                                                                                          \
+            k_render_parity<VT, J, true><<<grid, block, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P);  \
+        else                                                                                                    \
+            k_render_parity<VT, J, false><<<grid, block, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P); \
+    } while (0)
     if (S.julia)
-        k_render_parity<kF32, true><<<grid, block, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P);
+        VP_PARITY(kF32, true);
     else if (S.voxel_type == kU8)
-        k_render_parity<kU8, false><<<grid, block, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P);
+        VP_PARITY(kU8, false);
     else if (S.voxel_type == kF16)
-        k_render_parity<kF16, false><<<grid, block, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P);
+        VP_PARITY(kF16, false);
     else
-        k_render_parity<kF32, false><<<grid, block, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P);
+        VP_PARITY(kF32, false);
+#undef VP_PARITY
     return cudaGetLastError();
 }
 }  // namespace vp

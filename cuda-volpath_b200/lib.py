@@ -49,6 +49,7 @@ SIGNATURES = {
     "vp_set_filter": (c_int, [c_vp, c_int]),
     "vp_set_envmap": (c_int, [c_vp, c_fp, c_int, c_int]),
     "vp_set_sun": (c_int, [c_vp, c_fp, c_fp]),
+    "vp_set_env_sampling": (c_int, [c_vp, c_int]),
     "vp_set_inv_view": (c_int, [c_vp, c_fp]),
     "vp_precompute_opacity": (c_int, [c_vp, c_fp]),
     "vp_free_volume": (c_int, [c_vp]),

@@ -77,6 +77,10 @@ class Renderer:
         d, p = np.ascontiguousarray(sun_dir, np.float32), np.ascontiguousarray(sun_power, np.float32)
         _l.check(self.L.vp_set_sun(self.h, _fp(d), _fp(p)))
 
+    def set_env_sampling(self, enable):
+        """The reference's PASSIVE_ENVMAP switch (K.cu:21): True = env-map importance sampling + one-sample MIS."""
+        _l.check(self.L.vp_set_env_sampling(self.h, int(bool(enable))))
+
     def copy_inv_view_matrix(self, m12):
         m = np.ascontiguousarray(m12, np.float32)
         assert m.size == 12

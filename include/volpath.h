@@ -96,6 +96,10 @@ int vp_set_julia(vp_context* ctx);
 int vp_set_filter(vp_context* ctx, int linear);                                   /* set_texture_filter_mode */
 int vp_set_envmap(vp_context* ctx, const float* rgba, int width, int height);     /* init_envmap, host ptr */
 int vp_set_sun(vp_context* ctx, const float* dir3, const float* power3);          /* set_sun */
+/* the reference's PASSIVE_ENVMAP switch (K.cu:21), a compile-time macro there: 0 (default, as shipped) = the environment
+ * is picked up by escaping paths; enable != 0 = env-map importance sampling + one-sample MIS with phase sampling at
+ * every scatter event (K.cu:904-1034, 2220-2297); the CDF tables are built like init_envmap builds them */
+int vp_set_env_sampling(vp_context* ctx, int enable);
 int vp_set_inv_view(vp_context* ctx, const float* m12);                           /* copy_inv_view_matrix */
 int vp_precompute_opacity(vp_context* ctx, const float* light_dir3);              /* precompute_opacity */
 int vp_free_volume(vp_context* ctx);                                              /* free_cuda_buffers */

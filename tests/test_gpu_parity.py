@@ -452,3 +452,64 @@ def test_wavefront_form_julia(R, vp):
     a = R.render(P, 0, 8, mode=vp.MODE_FAST)
     b = R.render(P, 0, 8, mode=vp.MODE_WAVE)
     assert np.array_equal(a[..., 3], b[..., 3]) and np.allclose(a[..., :3], b[..., :3], rtol=2e-5, atol=1e-6)
+
+
+# ---- env-map importance sampling + one-sample MIS (the reference's PASSIVE_ENVMAP 0 variant) ---------------------
+def _mis_env():
+    rs = np.random.RandomState(5)
+    env = (rs.rand(8, 16, 4).astype(np.float32) ** 3 * 4).astype(np.float32)
+    env[..., 3] = 1
+    env[6:, :, :3] = 0
+    return env
+
+
+@pytest.mark.parametrize("name,pkey", [("gray", "param_default"), ("chroma", "param_chroma")])
+def test_env_sampling_parity_vs_reference_golden(R, golden, vp, name, pkey):
+    P = param_from_bytes(vp, golden[pkey])
+    setup_renderer(R, vp, golden["vol_f32"], False, True, env=golden["mis_env"])
+    R.set_env_sampling(True)
+    try:
+        got = R.render(P, 0, 3, mode=vp.MODE_PARITY)
+    finally:
+        R.set_env_sampling(False)
+    assert match_fraction(got, golden["render_mis_" + name + "_f0_3"], 1e-5) >= 0.93
+
+
+def test_env_sampling_parity_vs_reference_cuda_kernel(R, oracle, vp):
+    """The reference's own kernel compiled with PASSIVE_ENVMAP 0, same GPU, point filter: fixed-seed traces, 1e-5."""
+    ref = _ref_cuda_mis()
+    vol = small_cloud(oracle, (56, 40, 64))
+    env, sd, sp = vp.default_sunsky()
+    env = np.ascontiguousarray(env[::8, ::8])  # 128 x 64 map: the CDF search depth of a real map, small enough for a test
+    P = vp.default_param(96, 64)
+    P.density = 300.0
+    setup_scene(ref, vp, vol, False, False, env=env)
+    setup_renderer(R, vp, vol, False, False, env=env)
+    R.set_env_sampling(True)
+    try:
+        want = ref.render(P, 0, 4)
+        got = R.render(P, 0, 4, mode=vp.MODE_PARITY)
+        assert want[..., 3].sum() > 0
+        assert match_fraction(got, want, 1e-5) >= 0.97
+        # production renderer, same estimator in distribution
+        a = R.render(P, 0, 512, mode=vp.MODE_PARITY)
+        b = R.render(P, 512, 512, mode=vp.MODE_PARITY)
+        f = R.render(P, 0, 512, mode=vp.MODE_FAST)
+        for sl in (np.s_[..., :3], np.s_[..., 3]):
+            ma, mb, mf = a[sl].mean(), b[sl].mean(), f[sl].mean()
+            assert abs(mf - 0.5 * (ma + mb)) <= 3 * abs(ma - mb) + 0.004 * ma, (ma, mb, mf)
+        with pytest.raises(vp.VolpathError, match="wavefront"):
+            R.render(P, 0, 1, mode=vp.MODE_WAVE)
+    finally:
+        R.set_env_sampling(False)
+    # the two estimators (env picked up by escaping paths / sampled at every scatter event) agree in the mean
+    p = R.render(P, 0, 512, mode=vp.MODE_FAST)
+    assert abs(p[..., :3].mean() - f[..., :3].mean()) <= 0.03 * p[..., :3].mean()
+
+
+def _ref_cuda_mis():
+    from oraclelib import RefCuda, have_ref
+
+    if not have_ref("libvolpath_ref_cuda_mis.so"):
+        pytest.skip("oracle/_ref/libvolpath_ref_cuda_mis.so not built")
+    return RefCuda(mis=True)

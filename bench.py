@@ -156,7 +156,21 @@ def _host_reference_run(args, julia, name):
         ref.render(P, 0, fps, accum=acc)
     dt = time.perf_counter() - t0
     value = W * H * fps * args.steps / dt
-    return value, dt, dict(value=value, unit="path-samples/s", cores=cores, kind=kind, sample=sample % fps)
+    # the same loop on ONE host thread (north_star: "single-threaded plus OpenMP"), one frame
+    single = None
+    try:
+        import ctypes as _c
+
+        omp = _c.CDLL("libgomp.so.1")
+        omp.omp_set_num_threads(1)
+        t1 = time.perf_counter()
+        ref.render(P, 0, 1, accum=acc)
+        single = W * H / (time.perf_counter() - t1)
+        omp.omp_set_num_threads(cores)
+    except Exception:
+        pass
+    return value, dt, dict(value=value, unit="path-samples/s", cores=cores, kind=kind, sample=sample % fps,
+                           single_thread_value=single)
 
 
 def main():

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--density", type=float, default=800.0)
     ap.add_argument("--albedo", type=float, default=1.0)
     ap.add_argument("--material", type=int, default=-1, help="index into the reference's Mat() table")
+    ap.add_argument("--julia", action="store_true", help="config C1: the no-OpenVDB build (procedural Julia set)")
     args = ap.parse_args()
     # the reference printf()s to stdout
     sys.stdout.flush()
@@ -49,18 +50,24 @@ def main():
     env, sd, sp = vp.default_sunsky()
     view = vp.inv_view_matrix()
     r = vp.Renderer(args.device)
-    r.generate_cloud(nx, ny, nz, seed=0, store=vp.VOXEL_F32, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL, keep_dense=True)
+    if args.julia:
+        r.set_julia()
+        ref = RefCuda(julia=True)
+        ref.set_julia()
+    else:
+        r.generate_cloud(nx, ny, nz, seed=0, store=vp.VOXEL_F32, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL, keep_dense=True)
     r.set_texture_filter_mode(True)
     r.init_envmap(env)
     r.set_sun(sd, sp)
     r.copy_inv_view_matrix(view)
     r.precompute_opacity(sd)
-    bv = torch.from_numpy(r.bounds_voxel()).cuda()
-    ref = RefCuda()
-    rc = ref.L.ref_init_volume_device(r.dense_volume_ptr(), bv.data_ptr(), nx, ny, nz, 0, None, None, 1)
-    assert rc == 0, rc
-    del bv
-    ref.dims, ref.quantized = (nx, ny, nz), False
+    if not args.julia:
+        bv = torch.from_numpy(r.bounds_voxel()).cuda()
+        ref = RefCuda()
+        rc = ref.L.ref_init_volume_device(r.dense_volume_ptr(), bv.data_ptr(), nx, ny, nz, 0, None, None, 1)
+        assert rc == 0, rc
+        del bv
+        ref.dims, ref.quantized = (nx, ny, nz), False
     ref.set_envmap(env)
     ref.set_sun(sd, sp)
     ref.set_inv_view(view)
@@ -85,8 +92,9 @@ def main():
     ms_ours = r.last_kernel_ms()
     n = W * H * args.frames
     a, b = acc_r.cpu().numpy() / args.frames, acc_o.cpu().numpy() / args.frames
-    out = {"workload": "C2 cloud family %dx%dx%d fp32, %dx%d, frames %d..%d, density %g, albedo %g, material %d"
-                       % (nx, ny, nz, W, H, warm, warm + args.frames - 1, args.density, args.albedo, args.material),
+    scene = "C1 Julia set (no-OpenVDB build)" if args.julia else "C2 cloud family %dx%dx%d fp32" % (nx, ny, nz)
+    out = {"workload": "%s, %dx%d, frames %d..%d, density %g, albedo %g, material %d"
+                       % (scene, W, H, warm, warm + args.frames - 1, args.density, args.albedo, args.material),
            "reference_kernel_path_samples_per_s": n / (ms_ref * 1e-3), "ours_path_samples_per_s": n / (ms_ours * 1e-3),
            "speedup": ms_ref / ms_ours, "ms_reference": ms_ref, "ms_ours": ms_ours,
            "image_mean_rel_diff": float(abs(a[..., :3].mean() - b[..., :3].mean()) / a[..., :3].mean()),

@@ -14,6 +14,7 @@ ap.add_argument("--dims", type=int, nargs=3, default=[497, 338, 612])
 ap.add_argument("--image", type=int, nargs=2, default=[1920, 1080])
 ap.add_argument("--frames", type=int, default=16)
 ap.add_argument("--mode", default="fast")
+ap.add_argument("--material", type=int, default=-1)
 a = ap.parse_args()
 import torch  # noqa: E402
 
@@ -27,6 +28,8 @@ r.copy_inv_view_matrix(vp.inv_view_matrix())
 r.precompute_opacity(sd)
 W, H = a.image
 P = vp.default_param(W, H)
+if a.material >= 0:
+    P = vp.mat(P, *vp.MATERIALS[a.material])
 acc = torch.zeros(H, W, 4, device="cuda")
 r.set_stats(True)
 r.counters(reset=True)

@@ -30,15 +30,23 @@
 namespace vp
 {
 constexpr int      kFastThreads  = 128;
-// 10 CTAs x 128 threads x 48 registers per SM (40 warps) and two walk steps per vote measured best on B200
-// (8 / 9 / 10 CTAs: 820 / 878 / 903 M path-samples/s; 1 / 2 / 3 steps per vote: 878 / 907 / 896; both: 937)
+// Occupancy: the kernel waits on dependent loads (ncu: 7 of 15 stall cycles per issue are long-scoreboard), so warps
+// per SM matter.  8 / 9 / 10 CTAs of 128 threads: 820 / 878 / 903 M path-samples/s (1/4-dims cloud); with the cold
+// lane state in shared memory (VP_COLD_SMEM) the step block fits 40 registers and 12 CTAs (48 warps) are resident:
+// full C2 volume 894 -> 935 M/s (no change on the small cloud).  Two walk steps per vote: +3 %.
+#ifndef VP_COLD_SMEM
+#define VP_COLD_SMEM 1
+#endif
 #ifndef VP_CTAS_PER_SM
-#define VP_CTAS_PER_SM 10
+#define VP_CTAS_PER_SM (VP_COLD_SMEM ? 12 : 10)
 #endif
 #ifndef VP_STEP_REPS
 #define VP_STEP_REPS 2
 #endif
+
 constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
+// chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 11 CTAs; the MIS variant 8
+__host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis) { return mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 11 ? 11 : kFastCtasPerSm)); }
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a
@@ -154,6 +162,25 @@ __device__ __forceinline__ void item_to_sample(unsigned long long item, uint32_t
     y = (tile / tiles_x) * 4 + (p >> 3);
 }
 
+// "cold" lane state -- touched at scatter / segment / path events only, never in a walk step -- can live in shared
+// memory (one word per field per thread, field-major: conflict-free), which takes it out of the register budget of the
+// step block.  Cold3 / ColdF read and write like a float3 / float.
+struct Cold3
+{
+    float* p;
+    __device__ __forceinline__ operator float3() const { return f3(p[0], p[kFastThreads], p[2 * kFastThreads]); }
+    __device__ __forceinline__ void operator=(float3 v) const
+    {
+        p[0] = v.x; p[kFastThreads] = v.y; p[2 * kFastThreads] = v.z;
+    }
+};
+struct ColdF
+{
+    float* p;
+    __device__ __forceinline__ operator float() const { return *p; }
+    __device__ __forceinline__ void operator=(float v) const { *p = v; }
+};
+
 __device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t pix, float3 L, int n, float brightness)
 {
     // Q9: per-sample clamp (K.cu:2315-2316); one red.global.add.v4.f32
@@ -162,7 +189,7 @@ __device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t 
 }
 
 template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS>
-__global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
+__global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
                                                                   unsigned long long* __restrict__ d_work,
@@ -179,9 +206,18 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
     // warp-uniform claim window
     unsigned long long w_next = 0, w_end = 0;
     // lane state
+#if VP_COLD_SMEM
+    __shared__ float cold[12 * kFastThreads];
+    float*           cb = cold + threadIdx.x;
+    const Cold3      L{cb}, pend{cb + 3 * kFastThreads}, C{cb + 6 * kFastThreads};
+    const ColdF      t_exit{cb + 9 * kFastThreads}, ph{cb + 10 * kFastThreads}, dmax{cb + 11 * kFastThreads};
+    float3           o = f3(0.f), s = f3(0.f), T = f3(1.f);
+    float            dist = 0.f, lim = 0.f, inv = 0.f, dens = 0.f, maj = 0.f, sigc = 0.f;
+#else
     float3   o = f3(0.f), s = f3(0.f), pend = f3(0.f), T = f3(1.f), L = f3(0.f);
     float3   C = f3(0.f);  // MIS only: radiance the pending env-direction walk will add if it survives
     float    dist = 0.f, lim = 0.f, inv = 0.f, dens = 0.f, maj = 0.f, sigc = 0.f, t_exit = 0.f, ph = 0.f, dmax = 0.f;
+#endif
     int      n = 0;
     uint32_t st = kModePath, pix = 0;
     Philox   rng{0, 0, 0};
@@ -231,8 +267,8 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                     // sun disk (acosf + atanf + one texel), then one vector atomic
                     if (STATS) c_env++;
                     // K.cu:2026-2030: with env-map sampling the environment is picked up by escaping paths at depth 0 only
-                    if (!MIS || n == 0) L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
-                    accumulate(d_sum, pix, L, n, P.brightness);
+                    if (!MIS || n == 0) L = float3(L) + background(S, s, n) * (GRAY ? f3(T.x) : T);
+                    accumulate(d_sum, pix, float3(L), n, P.brightness);
                     st = kModePath;
                 }
                 if (item >= n_items)
@@ -269,23 +305,25 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                     t_exit = (tf > tn && tf >= 1e-3f) ? tf : -1.0f;
                 }
                 bool found = false;
-                while (dist < t_exit)
+                const float t_ex = t_exit;
+                while (dist < t_ex)
                 {
                     if (STATS) c_seg++;
-                    float  seg_end = JULIA ? t_exit : fminf(dist + kSearchRadius, t_exit);
+                    float  seg_end = JULIA ? t_ex : fminf(dist + kSearchRadius, t_ex);
                     float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at(S, o + s * dist);
                     if (bnd.x <= 0.0f)
                     {
                         // no medium within reach: the walk passes with probability 1; -bnd.x is how far it may go
                         // in any direction without leaving vacuum (breadth-first distance over the bound cells)
-                        dist = fminf(dist + fmaxf(kSearchRadius, -bnd.x), t_exit);
+                        dist = fminf(dist + fmaxf(kSearchRadius, -bnd.x), t_ex);
                         continue;
                     }
-                    dmax = fmaxf(1e-4f, bnd.x);
+                    const float dmx = fmaxf(1e-4f, bnd.x);
+                    dmax            = dmx;
                     // reduced scattering after 5 bounces (K.cu:2039-2044)
                     float sr = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                     dens     = ((1 - sr) + sr * (1 - P.g)) * P.density;
-                    maj      = max_sig_t * dens * dmax;
+                    maj      = max_sig_t * dens * dmx;
                     lim      = seg_end;
                     st       = kModeStep;
                     if (bnd.y > 0.0f)  // analog decomposition (K.cu:2048-2054, Q2)
@@ -362,23 +400,23 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                             // sun walk done -> MIS stage; MIS walk done -> direction sampling stage
                             if (st & kMisWalk)
                             {
-                                L  = L + C * a;
+                                L  = float3(L) + float3(C) * a;
                                 st = kModeScat | kScatC;
                             }
                             else
                             {
-                                L  = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
+                                L  = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);
                                 st = kModeScat | kScatB;
                             }
                         }
                         else
                         {
-                            L  = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
-                            s  = pend;
+                            L  = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);
+                            s  = float3(pend);
                             st = kModeSeg | kNeedRay;
                             if (n >= kMaxDepth)
                             {
-                                accumulate(d_sum, pix, L, n, P.brightness);
+                                accumulate(d_sum, pix, float3(L), n, P.brightness);
                                 st = kModePath;
                             }
                         }
@@ -442,7 +480,8 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                 float  sr_pre = fmaxf(0.0f, fminf(1.0f, (n - 1 - 5) * 0.066666666666666666667f));
                 float  g      = (1 - sr_pre) * P.g;
                 float3 ft, fb;
-                make_frame(pend, ft, fb);
+                const float3 din = pend;
+                make_frame(din, ft, fb);
                 if (st & kScatB)
                 {
                     // one-sample MIS between phase-function and env-map sampling (K.cu:2220-2297)
@@ -454,9 +493,9 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                     if (rsel < 0.5f)
                     {
                         float3 ls = hg_sample_local_fast(g, u, v);
-                        dir       = ft * ls.x + fb * ls.y + pend * ls.z;
+                        dir       = ft * ls.x + fb * ls.y + din * ls.z;
                         envc      = eval_envmap(S, dir);
-                        float pdf_brdf = hg_eval_fast(g, dot3(pend, dir));
+                        float pdf_brdf = hg_eval_fast(g, dot3(din, dir));
                         float pdf_env  = pdf_envmap(S, envc);
                         float weight   = __fdividef(pdf_brdf * 0.5f, pdf_brdf * 0.5f + pdf_env * 0.5f) * 2.0f;
                         C              = envc * ((GRAY ? f3(T.x) : T) * weight);
@@ -466,7 +505,7 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                         float pdf_env = sample_envmap(S, u, v, envc);
                         ok            = pdf_env > 0.0f;  // (the reference `continue`s here, K.cu:2266: probability ~2^-23)
                         dir           = uv_to_dir(u, v);
-                        float pb      = hg_eval_fast(g, dot3(pend, dir));
+                        float pb      = hg_eval_fast(g, dot3(din, dir));
                         float weight  = __fdividef(pdf_env * 0.5f, pdf_env * 0.5f + pb * 0.5f) * 2.0f;
                         C             = envc * ((GRAY ? f3(T.x) : T) * (__fdividef(pb, pdf_env) * weight));
                     }
@@ -477,7 +516,7 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                         box_slabs_fast(S, o, s, tn, tf);
                         dist = 0.0f;
                         lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
-                        inv  = __fdividef(1.0f, max_sig_t * dens * dmax);
+                        inv  = __fdividef(1.0f, max_sig_t * dens * float(dmax));
                         st   = kModeStep | kShadow | kMisWalk;
                     }
                     else
@@ -488,11 +527,11 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                     float r0, r1;
                     rng.draw(r0, r1);
                     float3 l = hg_sample_local_fast(g, r0, r1);
-                    s        = normalize3(ft * l.x + fb * l.y + pend * l.z);
+                    s        = normalize3(ft * l.x + fb * l.y + din * l.z);
                     st       = kModeSeg | kNeedRay;
                     if (n >= kMaxDepth)
                     {
-                        accumulate(d_sum, pix, L, n, P.brightness);
+                        accumulate(d_sum, pix, float3(L), n, P.brightness);
                         st = kModePath;
                     }
                 }
@@ -523,16 +562,16 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                     if (STATS) c_op++;
                     float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, o, false) : 0.0f;
                     float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
-                    L          = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
+                    L          = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);
                     if (MIS)
                         st = kModeScat | kScatB;
                     else
                     {
-                        s  = pend;
+                        s  = float3(pend);
                         st = kModeSeg | kNeedRay;
                         if (n >= kMaxDepth)
                         {
-                            accumulate(d_sum, pix, L, n, P.brightness);
+                            accumulate(d_sum, pix, float3(L), n, P.brightness);
                             st = kModePath;
                         }
                     }
@@ -540,7 +579,7 @@ __global__ void __launch_bounds__(kFastThreads, MIS ? 8 : kFastCtasPerSm) k_rend
                 else
                 {
                     // shadow walk toward the sun with the LOCAL majorant (Q1), K.cu:2173-2208
-                    inv = __fdividef(1.0f, max_sig_t * dens * dmax);
+                    inv = __fdividef(1.0f, max_sig_t * dens * float(dmax));
                     s   = S.sun_dir;  // normalize(sun_dir * 1e10 - pos) up to rounding
                     float tn, tf;
                     box_slabs_fast(S, o, s, tn, tf);
@@ -577,7 +616,7 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
     unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
     unsigned long long want  = (items + kClaim - 1) / kClaim;                    // warps that can get a claim
     unsigned long long ctas  = (want + kFastThreads / 32 - 1) / (kFastThreads / 32);
-    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * (MIS ? 8 : kFastCtasPerSm) ? ctas : (unsigned long long)num_sms * (MIS ? 8 : kFastCtasPerSm));
+    unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS) ? ctas : (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS));
     if (grid < 1) grid = 1;
     if (d_stats)
         k_render_fast<VT, JULIA, GRAY, MIS, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);

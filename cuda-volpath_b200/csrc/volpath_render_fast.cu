@@ -45,8 +45,8 @@ constexpr int      kFastThreads  = 128;
 #endif
 
 constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
-// chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 11 CTAs; the MIS variant 8
-__host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis) { return mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 11 ? 11 : kFastCtasPerSm)); }
+// chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 10 CTAs (48 registers); the MIS variant 8
+__host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis) { return mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 10 ? 10 : kFastCtasPerSm)); }
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a

@@ -331,6 +331,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     }
 
     S.brick_words  = c->words;
+    S.stream_octets = c->octet_bytes > ((size_t)8 << 30) ? 1 : 0;  // pool >> 126 MB of L2: no reuse to protect
     S.brick_table  = c->table;
     S.octets       = c->octets;
     S.bounds_voxel = c->bounds_voxel;

@@ -42,6 +42,7 @@ struct Scene
     float3 bmin, bmax, l_inv;  // K.cu:155-159 (min, max, 1/(max-min))
     const uint2*    brick_words;   // per 32 bricks (x-fastest order): {occupancy bits, slot of the first set bit}
     const uint32_t* brick_table;   // flat slot table, kept only while it is small enough to live in L1/L2 (else null)
+    int             stream_octets; // octet pool >> L2: load octets with L2 evict_first (see ldg256_stream)
     const void*     octets;
     const float2*   bounds_voxel;  // [nz][ny][nx] (max,min)   -- parity
     const float2*   bounds_cell;   // [ncz][ncy][ncx] (max,min) -- fast; cell = (1 << cell_log2)^3 voxels
@@ -149,6 +150,45 @@ __host__ __device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1,
     o1 = c1;
 }
 
+// ---- L2 residency control (sm_100a) -------------------------------------------------------------
+// At full C2 the octet pool (54 GB) streams through the 126 MB L2 at > 3 TB/s and would evict the small tables every
+// path reads again and again (bound grid 103 MB, sun-clear 52 MB, rank directory 3 MB).  The production kernels
+// therefore load the tables with an L2 evict_last policy and -- when the pool is far larger than L2 -- the octets with
+// ONE 256-bit evict_first load (LDG.E.EFL2.256, Blackwell's 32-byte vector load) instead of two 128-bit ones.
+__device__ __forceinline__ uint64_t l2_policy_keep()
+{
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float2 ldg_keep(const float2* a)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(l2_policy_keep()));
+    return v;
+}
+__device__ __forceinline__ float ldg_keep(const float* a)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(l2_policy_keep()));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_keep(const uint2* a)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_policy_keep()));
+    return v;
+}
+__device__ __forceinline__ void ldg256_stream(const void* a, float v[8])
+{
+    uint32_t w[8];
+    asm volatile("ld.global.nc.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(a));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(w[i]);
+}
+
 // ---- octet store -------------------------------------------------------------------------------
 template <int VT> struct OctetBytes;
 template <> struct OctetBytes<kU8> { static constexpr int value = 8; };
@@ -192,7 +232,7 @@ __device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, i
     // the two dependent loads of a density fetch now hits L1/L2 instead of competing with the octets for L2.
     const uint32_t b   = (uint32_t)((bz * S.nby + by) * S.nbx + bx);  // < 2^31 bricks (dims <= 8184)
     if (S.brick_table) return __ldg(S.brick_table + b);  // small volumes: 4 MB of flat table is cache-resident anyway
-    const uint2    w   = __ldg(S.brick_words + (b >> 5));
+    const uint2    w   = ldg_keep(S.brick_words + (b >> 5));
     const uint32_t bit = 1u << (b & 31u);
     return (w.x & bit) ? w.y + __popc(w.x & (bit - 1u)) : kEmptyBrick;
 }

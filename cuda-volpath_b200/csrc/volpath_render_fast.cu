@@ -115,7 +115,10 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
     uint32_t slot = brick_slot(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;
-    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    if (VT == kF32 && S.stream_octets)
+        ldg256_stream(reinterpret_cast<const float4*>(S.octets) + cell_in_slot(slot, ix, iy, iz) * 2, v);
+    else
+        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
     float a = xb - fx, b = yb - fy, g = zb - fz;
     float c00 = fmaf(a, v[1] - v[0], v[0]);
     float c10 = fmaf(a, v[3] - v[2], v[2]);
@@ -141,7 +144,7 @@ __device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
 // than the reference's per-voxel window (and identical to it when cell_log2 == 0).
 __device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
 {
-    return __ldg(S.bounds_cell + bound_cell_index(S, pos));
+    return ldg_keep(S.bounds_cell + bound_cell_index(S, pos));
 }
 
 __device__ __forceinline__ float hg_eval_fast(float g, float c)
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     dist = 0.0f;
                     lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
                     // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
-                    if (!JULIA && S.sun_clear) lim = fminf(lim, __ldg(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
+                    if (!JULIA && S.sun_clear) lim = fminf(lim, ldg_keep(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
                     st   = kModeStep | kShadow;
                 }
             }

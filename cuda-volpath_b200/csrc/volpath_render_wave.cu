@@ -73,7 +73,10 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
     uint32_t slot = brick_slot(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;
-    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    if (VT == kF32 && S.stream_octets)
+        ldg256_stream(reinterpret_cast<const float4*>(S.octets) + cell_in_slot(slot, ix, iy, iz) * 2, v);
+    else
+        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
     float a = xb - fx, b = yb - fy, g = zb - fz;
     float c00 = fmaf(a, v[1] - v[0], v[0]);
     float c10 = fmaf(a, v[3] - v[2], v[2]);
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                 while (dist < t_exit)
                 {
                     float  seg_end = JULIA ? t_exit : fminf(dist + kSearchRadius, t_exit);
-                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : __ldg(S.bounds_cell + bound_cell_index(S, o + s * dist));
+                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : ldg_keep(S.bounds_cell + bound_cell_index(S, o + s * dist));
                     if (bnd.x <= 0.0f)
                     {
                         dist = fminf(dist + fmaxf(kSearchRadius, -bnd.x), t_exit);
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                     float tn, tf;
                     box_slabs_fast(S, o, s, tn, tf);
                     float lim = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
-                    if (!JULIA && S.sun_clear) lim = fminf(lim, __ldg(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
+                    if (!JULIA && S.sun_clear) lim = fminf(lim, ldg_keep(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
                     STF(F_INV, inv); STF(F_LIM, lim); STF(F_DIST, 0.0f); STF(F_PH, ph);
                     ST3(F_SX, s);
                     ST3(F_PX, pend);

@@ -153,28 +153,39 @@ __host__ __device__ __forceinline__ void philox2x32_10(uint32_t c0, uint32_t c1,
 // ---- L2 residency control (sm_100a) -------------------------------------------------------------
 // At full C2 the octet pool (54 GB) streams through the 126 MB L2 at > 3 TB/s and would evict the small tables every
 // path reads again and again (bound grid 103 MB, sun-clear 52 MB, rank directory 3 MB).  The production kernels
-// therefore load the tables with an L2 evict_last policy and -- when the pool is far larger than L2 -- the octets with
-// ONE 256-bit evict_first load (LDG.E.EFL2.256, Blackwell's 32-byte vector load) instead of two 128-bit ones.
+// therefore load the tables with an L2 evict_last policy (+0.7 %).  Loading the octets with ONE 256-bit evict_first load
+// (LDG.E.EFL2.256, Blackwell's 32-byte vector load) instead of two 128-bit ones was measured too and LOSES 4 %: the
+// walk re-reads neighbouring octets of the same 128-byte line within a few steps, so the pool does have short-term L2
+// reuse worth keeping.  The code path stays behind VP_L2_STREAM for the record.
 __device__ __forceinline__ uint64_t l2_policy_keep()
 {
     uint64_t p;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+#ifndef VP_L2_KEEP
+#define VP_L2_KEEP 1
+#endif
+#ifndef VP_L2_STREAM
+#define VP_L2_STREAM 0  // measured on the full C2 volume: no hints 939, keep only 946, stream only 900, both 907 M path-samples/s
+#endif
 __device__ __forceinline__ float2 ldg_keep(const float2* a)
 {
+    if (!VP_L2_KEEP) return __ldg(a);
     float2 v;
     asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(l2_policy_keep()));
     return v;
 }
 __device__ __forceinline__ float ldg_keep(const float* a)
 {
+    if (!VP_L2_KEEP) return __ldg(a);
     float v;
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(l2_policy_keep()));
     return v;
 }
 __device__ __forceinline__ uint2 ldg_keep(const uint2* a)
 {
+    if (!VP_L2_KEEP) return __ldg(a);
     uint2 v;
     asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_policy_keep()));
     return v;

@@ -115,7 +115,7 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
     uint32_t slot = brick_slot(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;
-    if (VT == kF32 && S.stream_octets)
+    if (VP_L2_STREAM && VT == kF32 && S.stream_octets)
         ldg256_stream(reinterpret_cast<const float4*>(S.octets) + cell_in_slot(slot, ix, iy, iz) * 2, v);
     else
         load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);

@@ -69,8 +69,9 @@ enum { VP_BOUNDS_VOXEL = 1, VP_BOUNDS_CELL = 2 };
 /* render modes of vp_render
  *   VP_MODE_PARITY : one thread per pixel, reference RNG (Wang hash + xoroshiro64*), reference draw
  *                    order and segmenting; observationally identical to render_kernel.
- *   VP_MODE_FAST   : tile-owning CTAs with per-lane path regeneration, Philox2x32-10 counter RNG, analytic
- *                    skip of the empty-space march; same estimator in distribution.
+ *   VP_MODE_FAST   : megakernel: persistent warps on one global work pool, warp-level event binning, Philox2x32-10
+ *                    counter RNG, exact skipping of the empty-space march and of vacuum; same estimator in
+ *                    distribution.
  *   VP_MODE_WAVE   : the wavefront form of VP_MODE_FAST: ray states as SoA pools in shared memory, batches of 32
  *                    same-event states compacted with ballot/popc; the SAME samples as VP_MODE_FAST. */
 enum { VP_MODE_PARITY = 0, VP_MODE_FAST = 1, VP_MODE_WAVE = 2 };

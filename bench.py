@@ -209,6 +209,15 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # keep fd 1 for the ONE JSON line: NCCL / library chatter (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -346,7 +355,7 @@ def main():
         line["cpu_baseline"] = j.get("cpu_baseline", j)
     if world == 1 and not args.no_ref_cuda and dims is not None:
         line["ref_cuda"] = ref_cuda_compare(local, fps)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -262,6 +263,10 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     // fast-renderer bound grid: cell edge = largest power of two <= max(1, D/6) voxels (<= 8)
     int cl = 0;
     while (cl < 3 && (2 << cl) * 6 <= D) cl++;
+    // up to 128 Mi voxels (1 GiB of bounds) the fast renderer simply uses the reference's own per-voxel windows: the
+    // reference estimator is biased by construction and its expectation moves with the window
+    if ((bounds_flags & VP_BOUNDS_EXACT) || N <= ((size_t)128 << 20)) cl = 0;
+    if (const char* f = getenv("VOLPATH_FORCE_CELL_LOG2")) cl = atoi(f) < 0 ? 0 : (atoi(f) > 3 ? 3 : atoi(f));  // experiments only
     const int cell = 1 << cl;
     S.cell_log2    = cl;
     S.ncx = (nx + cell - 1) >> cl; S.ncy = (ny + cell - 1) >> cl; S.ncz = (nz + cell - 1) >> cl;
@@ -325,7 +330,10 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         int         margin = need > cover ? (int)ceilf((need - cover) / cw) : 0;
         if (margin > 32) margin = 32;
         c->vac_margin = margin;
-        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, 63, margin, cw, 0));
+        // breadth-first depth: 63 cells, fewer on very fine grids (each level is a pass over all cells)
+        const int kmax = cells > ((size_t)48 << 20) ? 15 : 63;
+        if (margin > kmax - 1) margin = kmax - 1;
+        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, kmax, margin, cw, 0));
         VP_CUDA(cudaDeviceSynchronize());
         cudaFree(tmp);
     }
@@ -340,6 +348,11 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     S.have_opacity = 0;
     S.julia        = 0;
     c->have_volume = true;
+    if (getenv("VOLPATH_PARITY_USES_CELL_BOUNDS") && c->bounds_voxel && c->bounds_cell)  // experiments only
+    {
+        VP_CUDA(launch_expand_cell_bounds(S, c->bounds_voxel, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+    }
     return update_sun_clear(c);
 }
 
@@ -410,7 +423,8 @@ int vp_upload_volume(vp_context* c, const void* volume, int nx, int ny, int nz, 
     if (nx < 1 || ny < 1 || nz < 1 || nx > 8184 || ny > 8184 || nz > 8184) return fail(VP_ERR_INVALID, "bad volume dims %d %d %d", nx, ny, nz);
     if (src_voxel != VP_VOXEL_U8 && src_voxel != VP_VOXEL_F32) return fail(VP_ERR_UNSUPPORTED, "source voxels must be u8 or f32");
     if (store_voxel < VP_VOXEL_U8 || store_voxel > VP_VOXEL_F32) return fail(VP_ERR_INVALID, "bad store voxel type");
-    if (!(bounds_flags & (VP_BOUNDS_VOXEL | VP_BOUNDS_CELL))) return fail(VP_ERR_INVALID, "bounds_flags selects no bound grid");
+    if (!(bounds_flags & (VP_BOUNDS_VOXEL | VP_BOUNDS_CELL | VP_BOUNDS_EXACT))) return fail(VP_ERR_INVALID, "bounds_flags selects no bound grid");
+    if (bounds_flags & VP_BOUNDS_EXACT) bounds_flags |= VP_BOUNDS_CELL;
     VP_CUDA(cudaSetDevice(c->device));
     free_volume(c);
     const size_t N = (size_t)nx * ny * nz;
@@ -439,7 +453,8 @@ int vp_generate_cloud(vp_context* c, int nx, int ny, int nz, unsigned int seed, 
     if (!c) return fail(VP_ERR_INVALID, "null context");
     if (nx < 1 || ny < 1 || nz < 1 || nx > 8184 || ny > 8184 || nz > 8184) return fail(VP_ERR_INVALID, "bad volume dims %d %d %d", nx, ny, nz);
     if (store_voxel < VP_VOXEL_U8 || store_voxel > VP_VOXEL_F32) return fail(VP_ERR_INVALID, "bad store voxel type");
-    if (!(bounds_flags & (VP_BOUNDS_VOXEL | VP_BOUNDS_CELL))) return fail(VP_ERR_INVALID, "bounds_flags selects no bound grid");
+    if (!(bounds_flags & (VP_BOUNDS_VOXEL | VP_BOUNDS_CELL | VP_BOUNDS_EXACT))) return fail(VP_ERR_INVALID, "bounds_flags selects no bound grid");
+    if (bounds_flags & VP_BOUNDS_EXACT) bounds_flags |= VP_BOUNDS_CELL;
     VP_CUDA(cudaSetDevice(c->device));
     free_volume(c);
     const size_t N = (size_t)nx * ny * nz;

@@ -465,6 +465,25 @@ cudaError_t launch_sun_clear(const Scene& S, float3 sun, float step, float* out,
     return cudaGetLastError();
 }
 
+// experiment hook: give every voxel the bound of its cell of the fast grid (so the reference-faithful renderer can be
+// run on the widened windows and the effect of the coarser grid on the reference's own estimator measured)
+__global__ void __launch_bounds__(256) k_expand_cell_bounds(const __grid_constant__ Scene S, float2* __restrict__ bounds_voxel)
+{
+    size_t total = (size_t)S.nx * S.ny * S.nz;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    {
+        int    i = (int)(idx % S.nx), j = (int)((idx / S.nx) % S.ny), k = (int)(idx / ((size_t)S.nx * S.ny));
+        float2 b = S.bounds_cell[((size_t)(k >> S.cell_log2) * S.ncy + (j >> S.cell_log2)) * S.ncx + (i >> S.cell_log2)];
+        bounds_voxel[idx] = make_float2(b.x < 1e-20f ? 0.0f : b.x, b.y);
+    }
+}
+cudaError_t launch_expand_cell_bounds(const Scene& S, float2* bounds_voxel, cudaStream_t stream)
+{
+    size_t total = (size_t)S.nx * S.ny * S.nz;
+    k_expand_cell_bounds<<<grid_for(total, 256), 256, 0, stream>>>(S, bounds_voxel);
+    return cudaGetLastError();
+}
+
 // test helper: the opacity table as a dense [nz][ny][nx] array (0 where no brick stores the voxel)
 __global__ void __launch_bounds__(256) k_gather_opacity(const __grid_constant__ Scene S, float* __restrict__ dense_out)
 {

@@ -19,7 +19,7 @@ c_u64p = ctypes.POINTER(ctypes.c_ulonglong)
 VP_OK = 0
 VOXEL_U8, VOXEL_F16, VOXEL_F32 = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
-BOUNDS_VOXEL, BOUNDS_CELL = 1, 2
+BOUNDS_VOXEL, BOUNDS_CELL, BOUNDS_EXACT = 1, 2, 4
 MODE_PARITY, MODE_FAST, MODE_WAVE = 0, 1, 2
 
 

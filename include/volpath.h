@@ -61,10 +61,16 @@ enum { VP_MEM_HOST = 0, VP_MEM_DEVICE = 1 };
  *                     (src/volumeRender.cpp:1089-1267); needed by the parity renderer.
  *   VP_BOUNDS_CELL  : per cell of c^3 voxels, (max,min) over cell +-D voxels (= max/min of the per-voxel
  *                     bounds of the cell's voxels; conservative superset) -- used by the fast renderer.
- *                     c = largest power of two <= max(1, D/6), at most 8: the window is <= ~7 % wider than
- *                     the reference's and the grid stays ~100 MB at any resolution (c = 1: identical).
+ *                     c = 1 (identical to the reference's windows) up to 128 Mi voxels; above that the largest
+ *                     power of two <= max(1, D/6), at most 8: the window is <= ~7 % wider than the reference's
+ *                     and the grid stays ~100 MB at any resolution.
+ *   VP_BOUNDS_EXACT : VP_BOUNDS_CELL with c forced to 1: the fast renderer sees exactly the reference's windows
+ *                     (8 B/voxel).  The reference estimator is biased by construction and its
+ *                     expectation moves with the window: measured on the 1/4-dims cloud, c = 2 / 4 / 8 shift the mean
+ *                     scatter count by -0.4 / -1.1 / -1.8 % and the image mean by 4e-4 / 7e-4 / 1.4e-3 -- for the
+ *                     reference's OWN kernel fed those windows just the same.
  * The flags can be or-ed. */
-enum { VP_BOUNDS_VOXEL = 1, VP_BOUNDS_CELL = 2 };
+enum { VP_BOUNDS_VOXEL = 1, VP_BOUNDS_CELL = 2, VP_BOUNDS_EXACT = 4 };
 
 /* render modes of vp_render
  *   VP_MODE_PARITY : one thread per pixel, reference RNG (Wang hash + xoroshiro64*), reference draw

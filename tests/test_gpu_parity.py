@@ -64,8 +64,11 @@ def test_voxel_bounds_bit_exact_vs_reference_routine(R, golden, vp, tag):
 
 
 @pytest.mark.parametrize("dims,cell", [((56, 40, 64), 1), ((100, 20, 31), 1), ((9, 9, 9), 1), ((500, 12, 10), 2), ((1001, 9, 11), 4)])
-def test_bounds_ragged_grids_vs_oracle(R, oracle, vp, dims, cell):
+def test_bounds_ragged_grids_vs_oracle(R, oracle, vp, dims, cell, monkeypatch):
     vol = small_cloud(oracle, dims)
+    if cell > 1:
+        # small grids use the reference's own windows (c = 1); force the coarse rule (c = pow2 <= D/6) for this check
+        monkeypatch.setenv("VOLPATH_FORCE_CELL_LOG2", str(cell.bit_length() - 1))
     R.init_cuda(vol, False)
     bv = R.bounds_voxel()
     assert np.array_equal(bv, oracle.bounds_of(vol))

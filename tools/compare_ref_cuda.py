@@ -24,10 +24,11 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--truth-frames", type=int, default=0, help="extra reference frames for an RMSE ground truth")
     ap.add_argument("--device", type=int, default=0)
-    ap.add_argument("--mode", default="fast", choices=["fast", "wave"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "wave", "parity"])
     ap.add_argument("--density", type=float, default=800.0)
     ap.add_argument("--albedo", type=float, default=1.0)
     ap.add_argument("--material", type=int, default=-1, help="index into the reference's Mat() table")
+    ap.add_argument("--exact-bounds", action="store_true", help="VP_BOUNDS_EXACT: the fast renderer uses the reference's per-voxel windows")
     ap.add_argument("--julia", action="store_true", help="config C1: the no-OpenVDB build (procedural Julia set)")
     args = ap.parse_args()
     # the reference printf()s to stdout
@@ -43,7 +44,7 @@ def main():
     import cuda_volpath_b200 as vp
     from oraclelib import RefCuda
 
-    MODE = vp.MODE_WAVE if args.mode == "wave" else vp.MODE_FAST
+    MODE = {"wave": vp.MODE_WAVE, "parity": vp.MODE_PARITY}.get(args.mode, vp.MODE_FAST)
     torch.cuda.set_device(args.device)
     nx, ny, nz = args.dims
     W, H = args.image
@@ -55,7 +56,7 @@ def main():
         ref = RefCuda(julia=True)
         ref.set_julia()
     else:
-        r.generate_cloud(nx, ny, nz, seed=0, store=vp.VOXEL_F32, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL, keep_dense=True)
+        r.generate_cloud(nx, ny, nz, seed=0, store=vp.VOXEL_F32, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL | (vp.BOUNDS_EXACT if args.exact_bounds else 0), keep_dense=True)
     r.set_texture_filter_mode(True)
     r.init_envmap(env)
     r.set_sun(sd, sp)

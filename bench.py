@@ -301,6 +301,9 @@ def main():
     if rank == 0 or world > 1:
         h_sum = torch.zeros(H, W, 4, dtype=torch.float32).pin_memory()
         e2e_steps = max(2, min(args.steps, 4))
+        # one untimed call: first-use costs of the host-buffer path (device accumulator allocation, copy engines)
+        first, count, stride = vp.frames_for_rank(999 * fps * world, fps * world, rank, world)
+        vp.lib.check(r.L.vp_render_to_host(r.h, h_sum.data_ptr(), first, count, stride, ctypes.byref(P), vp.MODE_FAST))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

@@ -331,7 +331,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         if (margin > 32) margin = 32;
         c->vac_margin = margin;
         // breadth-first depth: 63 cells, fewer on very fine grids (each level is a pass over all cells)
-        const int kmax = cells > ((size_t)1 << 30) ? 3 : (cells > ((size_t)48 << 20) ? 15 : 63);
+        const int kmax = cells > ((size_t)1 << 30) ? 3 : (cells > ((size_t)160 << 20) ? 15 : 63);
         if (margin > kmax - 1) margin = kmax - 1;
         VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, kmax, margin, cw, 0));
         VP_CUDA(cudaDeviceSynchronize());

@@ -2,7 +2,7 @@
 // vp_precompute_opacity run once per volume or sun change (the B200 replacement of init_cuda's
 // cudaArray upload + CPU bound sweep, K.cu:354-420 / H.cpp:1089-1267, and of _precompute_opacity,
 // K.cu:483-524).  All of it is HBM-bound byte/compare work: coalesced along x, no tensor cores.
-#include "volpath_common.cuh"
+#include "volpath_fast_common.cuh"
 #include "volpath_kernels.h"
 
 namespace vp
@@ -551,10 +551,7 @@ __global__ void k_fetch_density(const __grid_constant__ Scene S, const float3* _
     if (parity)
         out[i] = fetch_density_parity<VT>(S, p);
     else
-    {
-        float3 q = (p - S.bmin) * S.l_inv;
-        out[i]   = fetch_density_fast<VT>(S, q.x * S.nx, q.y * S.ny, q.z * S.nz);
-    }
+        out[i] = density_at<VT, false>(S, p);  // the production fetch (positions inside the box)
 }
 cudaError_t launch_fetch_density(const Scene& S, const float3* pos, int n, int parity, float* out, cudaStream_t stream)
 {

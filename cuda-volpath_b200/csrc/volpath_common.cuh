@@ -296,38 +296,6 @@ __device__ __forceinline__ float fetch_density_parity(const Scene& S, float3 pos
     return __fadd_rn(__fmul_rn(ig, c0), __fmul_rn(g, c1));
 }
 
-// FAST density fetch: same sample point and neighbours, full-precision weights, fused lerps.
-// `vs` = voxel-space position p*N (already scaled by the caller).
-template <int VT>
-__device__ __forceinline__ float fetch_density_fast(const Scene& S, float x, float y, float z)
-{
-    float v[8];
-    if (!S.linear)
-    {
-        int      ix = clampi(__float2int_rd(x), 0, S.nx - 1) + 1, iy = clampi(__float2int_rd(y), 0, S.ny - 1) + 1,
-                 iz = clampi(__float2int_rd(z), 0, S.nz - 1) + 1;
-        uint32_t slot = brick_slot(S, ix, iy, iz);
-        if (slot == kEmptyBrick) return 0.0f;
-        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
-        return VT == kU8 ? v[0] * (1.0f / 255.0f) : v[0];
-    }
-    float xb = x - 0.5f, yb = y - 0.5f, zb = z - 0.5f;
-    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
-    float a = xb - fx, b = yb - fy, g = zb - fz;
-    int   ix = clampi((int)fx + 1, 0, S.nx), iy = clampi((int)fy + 1, 0, S.ny), iz = clampi((int)fz + 1, 0, S.nz);
-    uint32_t slot = brick_slot(S, ix, iy, iz);
-    if (slot == kEmptyBrick) return 0.0f;
-    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
-    float c00 = fmaf(a, v[1] - v[0], v[0]);
-    float c10 = fmaf(a, v[3] - v[2], v[2]);
-    float c01 = fmaf(a, v[5] - v[4], v[4]);
-    float c11 = fmaf(a, v[7] - v[6], v[6]);
-    float c0  = fmaf(b, c10 - c00, c00);
-    float c1  = fmaf(b, c11 - c01, c01);
-    float r   = fmaf(g, c1 - c0, c0);
-    return VT == kU8 ? r * (1.0f / 255.0f) : r;
-}
-
 // Procedural density of the reference's no-OpenVDB build (K.cu:84-140): quaternion Julia set,
 // q <- q^2 + c until |q|^2 >= 10 or 31 iterations; density = (iterations > 27).
 __device__ __forceinline__ float julia_density(float3 pos)

@@ -24,7 +24,7 @@
 //   * counter-based Philox2x32-10: key = pixel, counter = (draw index, frame); no carried RNG state.
 //   * density comes from the octet store: one table load + one 32/16/8-byte load per trilinear sample.
 //   * one vector atomic (red.global.add.v4.f32) per finished path into the float4 sum.
-#include "volpath_common.cuh"
+#include "volpath_fast_common.cuh"
 #include "volpath_kernels.h"
 
 namespace vp
@@ -90,81 +90,6 @@ struct Philox
     }
 };
 
-// density at a world position inside the box: one brick-table load + one octet load.  Positions come from
-// o + s * t with t inside the box interval, so cell' = floor(p * N - 0.5) + 1 is within [0, N] up to rounding;
-// a single unsigned range test replaces the six clamps of the texture unit's clamp addressing.
-template <int VT, bool JULIA>
-__device__ __forceinline__ float density_at(const Scene& S, float3 pos)
-{
-    if (JULIA) return julia_density(pos);
-    float v[8];
-    if (!S.linear)
-    {
-        int ix = __float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)) + 1, iy = __float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)) + 1,
-            iz = __float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)) + 1;
-        ix = clampi(ix, 1, S.nx); iy = clampi(iy, 1, S.ny); iz = clampi(iz, 1, S.nz);
-        uint32_t slot = brick_slot(S, ix, iy, iz);
-        if (slot == kEmptyBrick) return 0.0f;
-        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
-        return VT == kU8 ? v[0] * (1.0f / 255.0f) : v[0];
-    }
-    float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
-          zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
-    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
-    int   ix = (int)fx + 1, iy = (int)fy + 1, iz = (int)fz + 1;
-    if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
-    uint32_t slot = brick_slot(S, ix, iy, iz);
-    if (slot == kEmptyBrick) return 0.0f;
-    if (VP_L2_STREAM && VT == kF32 && S.stream_octets)
-        ldg256_stream(reinterpret_cast<const float4*>(S.octets) + cell_in_slot(slot, ix, iy, iz) * 2, v);
-    else
-        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
-    float a = xb - fx, b = yb - fy, g = zb - fz;
-    float c00 = fmaf(a, v[1] - v[0], v[0]);
-    float c10 = fmaf(a, v[3] - v[2], v[2]);
-    float c01 = fmaf(a, v[5] - v[4], v[4]);
-    float c11 = fmaf(a, v[7] - v[6], v[6]);
-    float c0  = fmaf(b, c10 - c00, c00);
-    float c1  = fmaf(b, c11 - c01, c01);
-    float r   = fmaf(g, c1 - c0, c0);
-    return VT == kU8 ? r * (1.0f / 255.0f) : r;
-}
-
-__device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
-{
-    // cell-space coordinates in one FMA per axis; the grid has < 2^31 cells
-    int i = clampi(__float2int_rd(fmaf(pos.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1);
-    int j = clampi(__float2int_rd(fmaf(pos.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1);
-    int k = clampi(__float2int_rd(fmaf(pos.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1);
-    return (uint32_t)((k * S.ncy + j) * S.ncx + i);
-}
-
-// local (max, min) at pos from the bound grid of the fast renderer: cells of (1 << cell_log2)^3 voxels, each
-// holding the (max, min) over the cell +-D voxels.  The cell edge is <= D/6, so the window is at most ~7 % wider
-// than the reference's per-voxel window (and identical to it when cell_log2 == 0).
-__device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
-{
-    return ldg_keep(S.bounds_cell + bound_cell_index(S, pos));
-}
-
-__device__ __forceinline__ float hg_eval_fast(float g, float c)
-{
-    float d = 1.0f + g * g - 2.0f * g * c;
-    return __fdividef(1.0f - g * g, 4.0f * kPi * d * sqrtf(d));
-}
-
-// item -> pixel: 8x4-pixel tiles, frames innermost per tile, so the 32 lanes of a fresh claim start on one tile
-__device__ __forceinline__ void item_to_sample(unsigned long long item, uint32_t n_frames, uint32_t tiles_x, uint32_t& x,
-                                               uint32_t& y, uint32_t& f)
-{
-    uint32_t p    = (uint32_t)(item & 31u);
-    uint32_t q    = (uint32_t)(item >> 5);  // the launcher keeps tiles * frames below 2^31
-    uint32_t tile = q / n_frames;
-    f             = q - tile * n_frames;
-    x = (tile % tiles_x) * 8 + (p & 7);
-    y = (tile / tiles_x) * 4 + (p >> 3);
-}
-
 // "cold" lane state -- touched at scatter / segment / path events only, never in a walk step -- can live in shared
 // memory (one word per field per thread, field-major: conflict-free), which takes it out of the register budget of the
 // step block.  Cold3 / ColdF read and write like a float3 / float.
@@ -183,13 +108,6 @@ struct ColdF
     __device__ __forceinline__ operator float() const { return *p; }
     __device__ __forceinline__ void operator=(float v) const { *p = v; }
 };
-
-__device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t pix, float3 L, int n, float brightness)
-{
-    // Q9: per-sample clamp (K.cu:2315-2316); one red.global.add.v4.f32
-    float4 v = make_float4(fmaxf(L.x * brightness, 0.0f), fmaxf(L.y * brightness, 0.0f), fmaxf(L.z * brightness, 0.0f), (float)n);
-    atomicAdd(d_sum + pix, v);
-}
 
 template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS>
 __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,

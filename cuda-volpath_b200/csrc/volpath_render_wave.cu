@@ -14,7 +14,7 @@
 //     states per warp) towards 28+ (profiles/), at the price of ~25 shared-memory operations per event.
 //   * the work pool (one atomic per 256 items), vacuum jumps, sun-clear clip, octet fetch and the vector-atomic
 //     accumulation are those of the megakernel.
-#include "volpath_common.cuh"
+#include "volpath_fast_common.cuh"
 #include "volpath_kernels.h"
 
 namespace vp
@@ -42,82 +42,6 @@ enum
     F_COUNT
 };
 constexpr int kWarpSmemWords = F_COUNT * kPool + kPool / 4 + 32 / 4;  // pool + mode bytes + batch bytes
-
-__device__ __forceinline__ void philox_draw(uint32_t key, uint32_t frame, uint32_t& ctr, float& u0, float& u1)
-{
-    uint32_t a, b;
-    philox2x32_10(ctr++, frame, key, a, b);
-    u0 = u32_to_unit_float(a);
-    u1 = u32_to_unit_float(b);
-}
-
-template <int VT, bool JULIA>
-__device__ __forceinline__ float density_at(const Scene& S, float3 pos)
-{
-    if (JULIA) return julia_density(pos);
-    float v[8];
-    if (!S.linear)
-    {
-        int ix = __float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)) + 1, iy = __float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)) + 1,
-            iz = __float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)) + 1;
-        ix = clampi(ix, 1, S.nx); iy = clampi(iy, 1, S.ny); iz = clampi(iz, 1, S.nz);
-        uint32_t slot = brick_slot(S, ix, iy, iz);
-        if (slot == kEmptyBrick) return 0.0f;
-        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
-        return VT == kU8 ? v[0] * (1.0f / 255.0f) : v[0];
-    }
-    float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
-          zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
-    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
-    int   ix = (int)fx + 1, iy = (int)fy + 1, iz = (int)fz + 1;
-    if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
-    uint32_t slot = brick_slot(S, ix, iy, iz);
-    if (slot == kEmptyBrick) return 0.0f;
-    if (VP_L2_STREAM && VT == kF32 && S.stream_octets)
-        ldg256_stream(reinterpret_cast<const float4*>(S.octets) + cell_in_slot(slot, ix, iy, iz) * 2, v);
-    else
-        load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
-    float a = xb - fx, b = yb - fy, g = zb - fz;
-    float c00 = fmaf(a, v[1] - v[0], v[0]);
-    float c10 = fmaf(a, v[3] - v[2], v[2]);
-    float c01 = fmaf(a, v[5] - v[4], v[4]);
-    float c11 = fmaf(a, v[7] - v[6], v[6]);
-    float c0  = fmaf(b, c10 - c00, c00);
-    float c1  = fmaf(b, c11 - c01, c01);
-    float r   = fmaf(g, c1 - c0, c0);
-    return VT == kU8 ? r * (1.0f / 255.0f) : r;
-}
-
-__device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
-{
-    int i = clampi(__float2int_rd(fmaf(pos.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1);
-    int j = clampi(__float2int_rd(fmaf(pos.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1);
-    int k = clampi(__float2int_rd(fmaf(pos.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1);
-    return (uint32_t)((k * S.ncy + j) * S.ncx + i);
-}
-
-__device__ __forceinline__ float hg_eval_fast(float g, float c)
-{
-    float d = 1.0f + g * g - 2.0f * g * c;
-    return __fdividef(1.0f - g * g, 4.0f * kPi * d * sqrtf(d));
-}
-
-__device__ __forceinline__ void item_to_sample(unsigned long long item, uint32_t n_frames, uint32_t tiles_x, uint32_t& x, uint32_t& y,
-                                               uint32_t& f)
-{
-    uint32_t p    = (uint32_t)(item & 31u);
-    uint32_t q    = (uint32_t)(item >> 5);
-    uint32_t tile = q / n_frames;
-    f             = q - tile * n_frames;
-    x = (tile % tiles_x) * 8 + (p & 7);
-    y = (tile / tiles_x) * 4 + (p >> 3);
-}
-
-__device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t pix, float3 L, int n, float brightness)
-{
-    float4 v = make_float4(fmaxf(L.x * brightness, 0.0f), fmaxf(L.y * brightness, 0.0f), fmaxf(L.z * brightness, 0.0f), (float)n);
-    atomicAdd(d_sum + pix, v);
-}
 
 #define FLD(f) pool[(f) * kPool + slot]
 #define LDF(f) FLD(f)

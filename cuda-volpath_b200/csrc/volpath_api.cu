@@ -608,6 +608,15 @@ int vp_resolve(vp_context* c, void* dst, const void* src, int size, float scale,
     return VP_OK;
 }
 
+int vp_accumulate(vp_context* c, void* d_dst, const void* d_src, int size, vp_stream stream)
+{
+    if (!c || !d_dst || !d_src || size < 0) return fail(VP_ERR_INVALID, "vp_accumulate: bad arguments");
+    VP_CUDA(cudaSetDevice(c->device));
+    VP_CUDA(launch_accumulate((float4*)d_dst, (const float4*)d_src, size, (cudaStream_t)stream));
+    c->launches++;
+    return VP_OK;
+}
+
 int vp_render_to_host(vp_context* c, void* h_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode)
 {
     if (!c || !h_sum || !p) return fail(VP_ERR_INVALID, "vp_render_to_host: bad arguments");

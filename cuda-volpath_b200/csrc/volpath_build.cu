@@ -527,6 +527,22 @@ __global__ void __launch_bounds__(256) k_gamma(float4* __restrict__ dst, const f
     float4 v = src[idx];
     dst[idx] = make_float4(powf(v.x * scale, gamma), powf(v.y * scale, gamma), powf(v.z * scale, gamma), 1.0f);
 }
+// dst += src: combining the per-GPU float4 sums of a sample-sharded render (single-process multi-GPU hosts copy the peer
+// sum with cudaMemcpyPeerAsync and add it here; multi-process hosts use ncclReduce / torch.distributed.reduce)
+__global__ void __launch_bounds__(256) k_accumulate(float4* __restrict__ dst, const float4* __restrict__ src, int size)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= size) return;
+    float4 a = dst[idx], b = src[idx];
+    dst[idx] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+cudaError_t launch_accumulate(float4* dst, const float4* src, int size, cudaStream_t stream)
+{
+    if (size <= 0) return cudaSuccess;
+    k_accumulate<<<(size + 255) / 256, 256, 0, stream>>>(dst, src, size);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve(float4* dst, const float4* src, int size, float scale, float gamma, cudaStream_t stream)
 {
     if (size <= 0) return cudaSuccess;

@@ -56,6 +56,7 @@ SIGNATURES = {
     "vp_render": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.POINTER(Param), c_int, c_vp]),
     "vp_render_to_host": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.POINTER(Param), c_int]),
     "vp_resolve": (c_int, [c_vp, c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float, c_vp]),
+    "vp_accumulate": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "vp_sync": (c_int, [c_vp]),
     "vp_get_bounds_voxel": (c_int, [c_vp, c_fp]),
     "vp_get_bounds_cell": (c_int, [c_vp, c_fp, ctypes.POINTER(c_int)]),

@@ -124,6 +124,9 @@ int vp_resolve(vp_context* ctx, void* d_dst_float4, const void* d_src_float4, in
  * added, and the result is copied back.  Synchronous. */
 int vp_render_to_host(vp_context* ctx, void* h_sum_float4, int first_frame, int n_frames, int frame_stride,
                       const vp_param* p, int mode);
+/* d_dst[i] += d_src[i] (float4, i < size), both on ctx's device: combines the per-GPU sums of a sample-sharded render in
+ * single-process hosts (cudaMemcpyPeerAsync the peer sum next to it, then add); multi-process hosts reduce with NCCL */
+int vp_accumulate(vp_context* ctx, void* d_dst_float4, const void* d_src_float4, int size, vp_stream stream);
 int vp_sync(vp_context* ctx);
 
 /* introspection for tests / benchmarks */

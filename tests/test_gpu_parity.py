@@ -412,6 +412,26 @@ def test_fast_renderer_frame_sharding_is_exact_in_scatter_counts(R, oracle, vp):
     assert np.allclose(parts[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
 
 
+def test_accumulate_combines_sharded_sums(R, oracle, vp):
+    import torch
+
+    vol = small_cloud(oracle, (48, 32, 56))
+    setup_renderer(R, vp, vol, False, True)
+    P = vp.default_param(64, 48)
+    P.density = 200.0
+    stream = torch.cuda.current_stream().cuda_stream
+    parts = [torch.zeros(48, 64, 4, device="cuda") for _ in range(2)]
+    for rank in range(2):
+        first, count, stride = vp.frames_for_rank(0, 7, rank, 2)
+        R.render_kernel(parts[rank].data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
+    vp.lib.check(R.L.vp_accumulate(R.h, parts[0].data_ptr(), parts[1].data_ptr(), 64 * 48, stream))
+    full = torch.zeros(48, 64, 4, device="cuda")
+    R.render_kernel(full.data_ptr(), 0, P, mode=vp.MODE_FAST, n_frames=7, stream=stream)
+    torch.cuda.synchronize()
+    assert torch.equal(parts[0][..., 3], full[..., 3])
+    assert torch.allclose(parts[0][..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
+
+
 def test_fast_counters_and_launch_count(R, oracle, vp):
     vol = small_cloud(oracle, (48, 32, 56))
     setup_renderer(R, vp, vol, False, True)

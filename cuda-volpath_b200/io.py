@@ -103,7 +103,9 @@ def dump_hdr(path, image):
 
 
 def load_hdr(path):
-    """Reader for the files dump_hdr writes (literal runs only) -> float32 [h, w, 3], rows in image order."""
+    """Radiance .hdr reader ("new RLE" scanlines with literal AND repeat runs, "-Y h +X w" orientation) -> float32
+    [h, w, 3] with row 0 = the LAST scanline of the file, i.e. the layout dump_hdr writes from (image.cpp:88) and the
+    reference's HDRLoader hands to init_envmap (src/hdr/HDRloader.cpp, volumeRender.cpp:220-257)."""
     with open(path, "rb") as f:
         raw = f.read()
     head, _, rest = raw.partition(b"\n\n")
@@ -122,10 +124,13 @@ def load_hdr(path):
             cursor = 0
             while cursor < w:
                 n = body[p]
-                if n > 128:
-                    raise ValueError("run-length runs are not produced by the reference writer")
-                out[j, cursor:cursor + n, k] = np.frombuffer(body[p + 1:p + 1 + n], np.uint8)
-                p += 1 + n
+                if n > 128:  # repeat run: the next byte n - 128 times
+                    n -= 128
+                    out[j, cursor:cursor + n, k] = body[p + 1]
+                    p += 2
+                else:        # literal run
+                    out[j, cursor:cursor + n, k] = np.frombuffer(body[p + 1:p + 1 + n], np.uint8)
+                    p += 1 + n
                 cursor += n
     e = out[..., 3].astype(np.int32)
     scale = np.where(e > 0, np.ldexp(np.float32(1.0), e - 128 - 8), 0).astype(np.float32)

@@ -72,3 +72,29 @@ def test_checkpoint_resume_is_exact(tmp_path, vp, oracle, golden):
     resumed = oracle.render(P, nxt, 3, accum=acc)
     assert np.array_equal(resumed.view(np.uint32), full.view(np.uint32))
     assert np.allclose(vp.io.resolve(full, 6), full / 6)
+
+
+def test_hdr_reader_handles_repeat_runs(tmp_path, vp):
+    """A hand-built Radiance file with run-length runs (count byte > 128), as real .hdr environment maps use."""
+    w, h = 10, 2
+    rgbe = np.zeros((h, w, 4), np.uint8)
+    rgbe[0, :, :] = [128, 64, 32, 129]          # constant row -> one repeat run per channel
+    rgbe[1, :5, :] = [10, 20, 30, 130]
+    rgbe[1, 5:, :] = [200, 100, 50, 127]
+    body = b""
+    for j in range(h):
+        body += bytes([2, 2, 0, w])
+        for k in range(4):
+            row = rgbe[j, :, k]
+            if j == 0:
+                body += bytes([128 + w, int(row[0])])
+            else:
+                body += bytes([128 + 5, int(row[0]), 5]) + row[5:].tobytes()
+    p = str(tmp_path / "rle.hdr")
+    open(p, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2 +X 10\n" + body)
+    img = vp.io.load_hdr(p)
+    assert img.shape == (2, 10, 3)
+    # file scanline 0 is image row h-1 (rows are stored top-down in the file, bottom-up in memory)
+    assert np.allclose(img[1, 3], np.array([128, 64, 32]) * 2.0 ** (129 - 136))
+    assert np.allclose(img[0, 2], np.array([10, 20, 30]) * 2.0 ** (130 - 136))
+    assert np.allclose(img[0, 7], np.array([200, 100, 50]) * 2.0 ** (127 - 136))

@@ -43,6 +43,12 @@ constexpr int      kFastThreads  = 128;
 #ifndef VP_STEP_REPS
 #define VP_STEP_REPS 2
 #endif
+#ifndef VP_STEP_MAXREPS
+#define VP_STEP_MAXREPS VP_STEP_REPS
+#endif
+#ifndef VP_STEP_MINLANES
+#define VP_STEP_MINLANES 16
+#endif
 
 constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
 // chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 10 CTAs (48 registers); the MIS variant 8
@@ -277,7 +283,10 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
         else if (pick == kModeStep)
         {
 #pragma unroll 1
-            for (int rep = 0; rep < VP_STEP_REPS; rep++)
+            for (int rep = 0; rep < VP_STEP_MAXREPS; rep++)
+            {
+            // after the guaranteed VP_STEP_REPS steps, keep stepping without a new vote while enough lanes still walk
+            if (rep >= VP_STEP_REPS && __popc(__ballot_sync(kFull, (st & kModeMask) == kModeStep)) < VP_STEP_MINLANES) break;
             if ((st & kModeMask) == kModeStep)
             {
                 // ---- one step of whichever walk this lane is on ----
@@ -391,6 +400,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                         st = kModeScat;
                     }
                 }
+            }
             }
         }
         else  // kModeScat

@@ -54,7 +54,7 @@ constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
 // chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 10 CTAs (48 registers); the MIS variant 8
 __host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis) { return mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 10 ? 10 : kFastCtasPerSm)); }
 constexpr uint32_t kFull         = 0xffffffffu;
-constexpr uint32_t kClaim        = 256;  // items per warp-level claim
+constexpr uint32_t kClaim        = 256;  // items per warp-level claim (large launches); small launches claim less, see launch_fast_t
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a
 // lower weight makes an expensive block wait for more lanes (tuned on B200, profiles/)
 #ifndef VP_W_PATH
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
                                                                   unsigned long long* __restrict__ d_work,
-                                                                  unsigned long long* __restrict__ d_stats)
+                                                                  unsigned long long* __restrict__ d_stats, uint32_t claim)
 {
     const uint32_t lane    = threadIdx.x & 31;
     const uint32_t tiles_x = (P.width + 7) >> 3, tiles_y = (P.height + 3) >> 2;
@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
             if (lane == 0) c_blk[pick - 1]++;
             if (mode == pick) c_act[pick - 1]++;
         }
-
         if (pick == kModePath)
         {
             const uint32_t needy = __ballot_sync(kFull, mode == kModePath);
@@ -175,11 +174,11 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
             if (cnt > avail)
             {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(d_work, (unsigned long long)kClaim);
+                if (lane == 0) base = atomicAdd(d_work, (unsigned long long)claim);
                 base   = __shfl_sync(kFull, base, 0);
                 item   = rank < avail ? w_next + rank : base + (rank - avail);
                 w_next = base + (cnt - avail);
-                w_end  = base + kClaim;
+                w_end  = base + claim;
             }
             else
             {
@@ -545,14 +544,19 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
     if (e != cudaSuccess) return e;
     // persistent grid: kFastCtasPerSm CTAs of 128 threads per SM, never more warps than claims
     unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
-    unsigned long long want  = (items + kClaim - 1) / kClaim;                    // warps that can get a claim
+    // claim size: 256 items per atomic when every warp will come back many times, down to 32 (one per lane) for small
+    // launches (e.g. one frame per launch, the reference host's own pattern) so that the pool keeps balancing the load
+    const unsigned long long warps_total = (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS) * (kFastThreads / 32);
+    unsigned long long       per_warp    = items / (warps_total * 16);
+    uint32_t                 claim       = (uint32_t)(per_warp < 32 ? 32 : (per_warp > kClaim ? kClaim : (per_warp / 32) * 32));
+    unsigned long long want  = (items + claim - 1) / claim;                      // warps that can get a claim
     unsigned long long ctas  = (want + kFastThreads / 32 - 1) / (kFastThreads / 32);
     unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS) ? ctas : (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS));
     if (grid < 1) grid = 1;
     if (d_stats)
-        k_render_fast<VT, JULIA, GRAY, MIS, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
+        k_render_fast<VT, JULIA, GRAY, MIS, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, claim);
     else
-        k_render_fast<VT, JULIA, GRAY, MIS, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
+        k_render_fast<VT, JULIA, GRAY, MIS, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
     return cudaGetLastError();
 }
 

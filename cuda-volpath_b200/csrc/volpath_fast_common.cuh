@@ -54,6 +54,25 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     return VT == kU8 ? r * (1.0f / 255.0f) : r;
 }
 
+// opacity table for the production renderers: same 9^3 apron blocks and trilinear weights as fetch_opacity (K.cu:541-542),
+// addressed like density_at (one FMA per axis, FMA lerps)
+__device__ __forceinline__ float opacity_at(const Scene& S, float3 pos)
+{
+    float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
+          zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    int   ix = clampi((int)fx + 1, 0, S.nx), iy = clampi((int)fy + 1, 0, S.ny), iz = clampi((int)fz + 1, 0, S.nz);
+    uint32_t slot = brick_slot(S, ix, iy, iz);
+    if (slot == kEmptyBrick) return 0.0f;  // only reachable where the density is zero around pos
+    const float* q = S.opacity + (size_t)slot * kOpBrickPad + (((iz & (kBrick - 1)) * 9 + (iy & (kBrick - 1))) * 9 + (ix & (kBrick - 1)));
+    float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 9), v3 = __ldg(q + 10);
+    float v4 = __ldg(q + 81), v5 = __ldg(q + 82), v6 = __ldg(q + 90), v7 = __ldg(q + 91);
+    float a = xb - fx, b = yb - fy, g = zb - fz;
+    float c00 = fmaf(a, v1 - v0, v0), c10 = fmaf(a, v3 - v2, v2), c01 = fmaf(a, v5 - v4, v4), c11 = fmaf(a, v7 - v6, v6);
+    float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
+    return fmaf(g, c1 - c0, c0);
+}
+
 __device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
 {
     // cell-space coordinates in one FMA per axis; the grid has < 2^31 cells

@@ -82,6 +82,7 @@ enum : uint32_t
     kMisWalk   = 1024,  // the shadow walk in progress is the one toward the MIS direction (else: toward the sun)
     kScatB     = 2048,  // sun NEE done: choose the MIS direction and start its shadow walk
     kScatC     = 4096,  // both NEE walks done: sample the scattered direction
+    kShadowDone = 8192,  // a sun shadow walk just ended: its contribution is added at the head of the segment block
 };
 
 struct Philox
@@ -220,7 +221,27 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
         }
         else if (pick == kModeSeg)
         {
-            if (mode == kModeSeg)
+            if (!MIS && (st & kShadowDone))
+            {
+                // a sun shadow walk ended (kill flags in st): add the sun's contribution, turn into the sampled direction
+                if (GRAY)
+                {
+                    if (!(st & kKillX)) L = float3(L) + S.sun_power * (T.x * float(ph));
+                }
+                else
+                {
+                    float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
+                    L        = float3(L) + S.sun_power * (T * float(ph) * a);
+                }
+                s  = float3(pend);
+                st = kModeSeg | kNeedRay;
+                if (n >= kMaxDepth)
+                {
+                    accumulate(d_sum, pix, float3(L), n, P.brightness);
+                    st = kModePath;
+                }
+            }
+            if ((st & kModeMask) == kModeSeg)
             {
                 if (st & kNeedRay)
                 {
@@ -281,16 +302,9 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
         }
         else if (pick == kModeStep)
         {
-#pragma unroll 1
-            for (int rep = 0; rep < VP_STEP_MAXREPS; rep++)
+            // ---- one step of whichever walk this lane is on ----
+            auto step = [&](float u0, float u1)
             {
-            // after the guaranteed VP_STEP_REPS steps, keep stepping without a new vote while enough lanes still walk
-            if (rep >= VP_STEP_REPS && __popc(__ballot_sync(kFull, (st & kModeMask) == kModeStep)) < VP_STEP_MINLANES) break;
-            if ((st & kModeMask) == kModeStep)
-            {
-                // ---- one step of whichever walk this lane is on ----
-                float u0, u1;
-                rng.draw(u0, u1);
                 dist += -__logf(u0) * inv;
                 const bool past = dist >= lim;
                 float3     pos  = o + s * (past ? lim : dist);
@@ -323,9 +337,9 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     }
                     if (past || (st & (kKillX | kKillY | kKillZ)) == (kKillX | kKillY | kKillZ))
                     {
-                        float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
                         if (MIS)
                         {
+                            float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
                             // sun walk done -> MIS stage; MIS walk done -> direction sampling stage
                             if (st & kMisWalk)
                             {
@@ -340,14 +354,10 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                         }
                         else
                         {
-                            L  = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);
-                            s  = float3(pend);
-                            st = kModeSeg | kNeedRay;
-                            if (n >= kMaxDepth)
-                            {
-                                accumulate(d_sum, pix, float3(L), n, P.brightness);
-                                st = kModePath;
-                            }
+                            // the sun contribution and the pending direction are taken up at the head of the segment
+                            // block, which this lane needs next anyway: there the few lanes that finish a shadow
+                            // walk in any one step (2 of 32, ncu) are batched with the other lanes that start a ray
+                            st = kModeSeg | kNeedRay | kShadowDone | (st & (kKillX | kKillY | kKillZ));
                         }
                     }
                 }
@@ -399,7 +409,18 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                         st = kModeScat;
                     }
                 }
-            }
+            };
+#pragma unroll 1
+            for (int rep = 0; rep < VP_STEP_MAXREPS; rep++)
+            {
+                // after the guaranteed VP_STEP_REPS steps, keep stepping without a new vote while enough lanes still walk
+                if (rep >= VP_STEP_REPS && __popc(__ballot_sync(kFull, (st & kModeMask) == kModeStep)) < VP_STEP_MINLANES) break;
+                if ((st & kModeMask) == kModeStep)
+                {
+                    float u0, u1;
+                    rng.draw(u0, u1);
+                    step(u0, u1);
+                }
             }
         }
         else  // kModeScat
@@ -490,8 +511,9 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 if ((int)rng.frame > 10 && n > 20)  // K.cu:2183: precomputed sun opacity
                 {
                     if (STATS) c_op++;
-                    float  tau = (!JULIA && S.have_opacity) ? fetch_opacity(S, o, false) : 0.0f;
-                    float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
+                    float  tau = (!JULIA && S.have_opacity) ? opacity_at(S, o) : 0.0f;
+                    float3 a   = GRAY ? f3(__expf(-sig_t.x * dens * tau))
+                                      : f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
                     L          = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);
                     if (MIS)
                         st = kModeScat | kScatB;

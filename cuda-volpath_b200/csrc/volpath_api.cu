@@ -92,6 +92,7 @@ static void scene_defaults(Scene& S)
     S.bmax = make_float3(1, 1, 1);
     S.l_inv = make_float3(0.5f, 0.5f, 0.5f);
     S.sun_dir = make_float3(0, 1, 0);
+    S.sun_inv = make_float3(1.0f / 0.0f, 1.0f, 1.0f / 0.0f);
     const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     memcpy(S.inv_view, id, sizeof(id));
     float fovx = 54.43;                                       // K.cu:1981
@@ -140,7 +141,7 @@ static void set_box(vp_context* c, int nx, int ny, int nz, const float* bmin, co
     S.l_inv    = make_float3(1.0f / (S.bmax.x - S.bmin.x), 1.0f / (S.bmax.y - S.bmin.y), 1.0f / (S.bmax.z - S.bmin.z));  // K.cu:313
     S.vs_scale = make_float3(S.l_inv.x * nx, S.l_inv.y * ny, S.l_inv.z * nz);
     S.vs_off   = make_float3(-S.bmin.x * S.vs_scale.x, -S.bmin.y * S.vs_scale.y, -S.bmin.z * S.vs_scale.z);
-    S.vs_off_lin = make_float3(S.vs_off.x - 0.5f, S.vs_off.y - 0.5f, S.vs_off.z - 0.5f);
+    S.vs_off_lin = make_float3(S.vs_off.x + 0.5f, S.vs_off.y + 0.5f, S.vs_off.z + 0.5f);
 }
 
 // host part of init_envmap for the PASSIVE_ENVMAP 0 variant (K.cu:1036-1070, 1144-1210; PRE_WARP 1): luminance * sin(phi),
@@ -527,6 +528,7 @@ int vp_set_sun(vp_context* c, const float* dir3, const float* power3)
     float scale = kPi * (r * r);
     S.sun_power = make_float3(S.sun_power_original.x * scale, S.sun_power_original.y * scale, S.sun_power_original.z * scale);
     S.sun_dir   = make_float3(dir3[0], dir3[1], dir3[2]);
+    S.sun_inv   = make_float3(1.0f / S.sun_dir.x, 1.0f / S.sun_dir.y, 1.0f / S.sun_dir.z);  // +-inf for an axis-parallel sun, as the slab test expects
     VP_CUDA(cudaSetDevice(c->device));
     return update_sun_clear(c);
 }

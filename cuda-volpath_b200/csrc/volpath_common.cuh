@@ -64,7 +64,8 @@ struct Scene
     // the shadow walk); clear_margin covers the offset between a point and its cell centre
     const float*    sun_clear;
     float           clear_margin;
-    float3          vs_off_lin;      // vs_off - 0.5 (texel-centre shift of the linear filter)
+    float3          vs_off_lin;      // vs_off - 0.5 + 1: position -> cell' coordinate of the linear filter (floor = cell', fraction = weight)
+    float3          sun_inv;         // 1 / sun_dir (slab test of the sun shadow ray without divisions)
     float3          cs_scale, cs_off;  // world -> bound-cell space
 };
 
@@ -452,6 +453,12 @@ __device__ __forceinline__ void camera_ray(const Scene& S, uint32_t x, uint32_t 
     d = normalize3(f3(dot3(dc, f3(M[0], M[1], M[2])), dot3(dc, f3(M[4], M[5], M[6])), dot3(dc, f3(M[8], M[9], M[10]))));
 }
 // fast-math variants for the production renderer (equal in distribution, not bit-for-bit)
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float3 hg_sample_local_fast(float g, float rnd0, float rnd1)
 {
     float cos_theta;
@@ -466,10 +473,26 @@ __device__ __forceinline__ float3 hg_sample_local_fast(float g, float rnd0, floa
     {
         cos_theta = 2.0f * rnd0 - 1.0f;
     }
-    float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+    float sin_theta = sqrt_approx(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
     float sp, cp;
     __sincosf(2.0f * kPi * rnd1, &sp, &cp);
     return f3(cp * sin_theta, sp * sin_theta, cos_theta);
+}
+// the reference's frame (K.cu:557-573) with the two cases of its helper axis written out
+__device__ __forceinline__ void make_frame_fast(float3 n, float3& t, float3& b)
+{
+    const bool big = fabsf(n.x) > 0.1f;
+    float3     c   = big ? f3(n.z, 0.0f, -n.x) : f3(0.0f, -n.z, n.y);
+    t              = c * rsqrtf(n.z * n.z + (big ? n.x * n.x : n.y * n.y));
+    b              = cross3(n, t);
+}
+// slab test with a precomputed reciprocal direction
+__device__ __forceinline__ void box_slabs_inv(const Scene& S, float3 o, float3 invR, float& largest_tmin, float& smallest_tmax)
+{
+    float3 tbot = invR * (S.bmin - o);
+    float3 ttop = invR * (S.bmax - o);
+    largest_tmin  = max_of(fmin3(ttop, tbot));
+    smallest_tmax = min_of(fmax3(ttop, tbot));
 }
 __device__ __forceinline__ void box_slabs_fast(const Scene& S, float3 o, float3 d, float& largest_tmin, float& smallest_tmax)
 {

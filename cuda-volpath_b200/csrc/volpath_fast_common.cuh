@@ -35,7 +35,7 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
           zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
     float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
-    int   ix = (int)fx + 1, iy = (int)fy + 1, iz = (int)fz + 1;
+    int   ix = (int)fx, iy = (int)fy, iz = (int)fz;  // vs_off_lin carries the + 1 of cell' = floor(p * N - 0.5) + 1
     if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
     uint32_t slot = brick_slot(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;
@@ -61,7 +61,7 @@ __device__ __forceinline__ float opacity_at(const Scene& S, float3 pos)
     float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
           zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
     float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
-    int   ix = clampi((int)fx + 1, 0, S.nx), iy = clampi((int)fy + 1, 0, S.ny), iz = clampi((int)fz + 1, 0, S.nz);
+    int   ix = clampi((int)fx, 0, S.nx), iy = clampi((int)fy, 0, S.ny), iz = clampi((int)fz, 0, S.nz);
     uint32_t slot = brick_slot(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;  // only reachable where the density is zero around pos
     const float* q = S.opacity + (size_t)slot * kOpBrickPad + (((iz & (kBrick - 1)) * 9 + (iy & (kBrick - 1))) * 9 + (ix & (kBrick - 1)));
@@ -93,7 +93,7 @@ __device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
 __device__ __forceinline__ float hg_eval_fast(float g, float c)
 {
     float d = 1.0f + g * g - 2.0f * g * c;
-    return __fdividef(1.0f - g * g, 4.0f * kPi * d * sqrtf(d));
+    return __fdividef(1.0f - g * g, 4.0f * kPi * d * sqrt_approx(d));
 }
 
 // item -> pixel: 8x4-pixel tiles, frames innermost per tile, so the 32 lanes of a fresh claim start on one tile

@@ -63,7 +63,7 @@ constexpr uint32_t kClaim        = 256;  // items per warp-level claim (large la
 #define VP_W_SEG 5
 #define VP_W_STEP 4
 #endif
-__device__ constexpr uint32_t kPickWeight[8] = {0, VP_W_PATH, VP_W_SCAT, VP_W_SEG, VP_W_STEP, 0, 0, 0};
+constexpr uint32_t kPickWeights = (VP_W_PATH << 4) | (VP_W_SCAT << 8) | (VP_W_SEG << 12) | (VP_W_STEP << 16);  // 4 bits per mode
 
 enum : uint32_t
 {
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
         // ---- vote: run the block the most lanes wait for (ties: step > segment > scatter > path) ----
         const uint32_t mode = st & kModeMask;
         const uint32_t same = __match_any_sync(kFull, mode);
-        const uint32_t key  = mode == kModeIdle ? 0u : (((__popc(same) * kPickWeight[mode]) << 3) | mode);
+        const uint32_t key  = ((__popc(same) * ((kPickWeights >> (mode * 4)) & 15u)) << 3) | mode;  // idle: 0
         const uint32_t pick = __reduce_max_sync(kFull, key) & 7u;
         if (pick == kModeIdle) break;
         if (STATS)
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 float  g      = (1 - sr_pre) * P.g;
                 float3 ft, fb;
                 const float3 din = pend;
-                make_frame(din, ft, fb);
+                make_frame_fast(din, ft, fb);
                 if (st & kScatB)
                 {
                     // one-sample MIS between phase-function and env-map sampling (K.cu:2220-2297)
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 else
                 {
                     float3 ft, fb;
-                    make_frame(s, ft, fb);
+                    make_frame_fast(s, ft, fb);
                     float r0, r1;
                     rng.draw(r0, r1);
                     float3 l = hg_sample_local_fast(g, r0, r1);
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     inv = __fdividef(1.0f, max_sig_t * dens * float(dmax));
                     s   = S.sun_dir;  // normalize(sun_dir * 1e10 - pos) up to rounding
                     float tn, tf;
-                    box_slabs_fast(S, o, s, tn, tf);
+                    box_slabs_inv(S, o, S.sun_inv, tn, tf);
                     dist = 0.0f;
                     lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
                     // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun

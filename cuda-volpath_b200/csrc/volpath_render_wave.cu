@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                 n++;
                 STU(F_N, (uint32_t)n);
                 float3 ft, fb;
-                make_frame(s, ft, fb);
+                make_frame_fast(s, ft, fb);
                 float ph = hg_eval_fast(g, dot3(s, S.sun_dir));
                 float r0, r1;
                 philox_draw(key, frame, ctr, r0, r1);

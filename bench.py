@@ -180,7 +180,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
-    ap.add_argument("--frames-per-step", type=int, default=64)
+    ap.add_argument("--frames-per-step", type=int, default=256,
+                    help="frames (sample indices) of the whole image per step = per launch; the default 4 steps x 256 are the 1024 spp of config C2")
     ap.add_argument("--store", default="f32", choices=["f32", "f16"])
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the host reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -337,7 +338,7 @@ def main():
     prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(prof):
         t = json.load(open(prof)).get(args.workload)
-        if t and fps == 64 and (W, H) == (1920, 1080):
+        if t and fps == t.get("frames", 64) and (W, H) == (1920, 1080):
             roof["traffic"] = t["dram_bytes_per_launch"]  # bytes per launch, same launch shape as `achieved`
             roof["traffic_source"] = t["source"]
         roof["algorithmic_bytes_per_launch"] = per_launch_bytes

@@ -62,6 +62,8 @@ struct vp_context
     float2*   bounds_cell = nullptr;
     float*    opacity     = nullptr;
     float*    sun_clear   = nullptr;
+    uint32_t* bounds_half = nullptr;     // half-precision copies for the production renderers (coarse cells only)
+    uint16_t* sun_clear_half = nullptr;
     float4*   env         = nullptr;
     std::vector<float> env_host;      // host copy of the env map (the CDF tables are built on the host, like init_envmap)
     float*    env_cdf_y   = nullptr;
@@ -112,6 +114,10 @@ static void free_volume(vp_context* c)
     dev_free(c->opacity);
     dev_free(c->sun_clear);
     c->S.sun_clear = nullptr;
+    dev_free(c->bounds_half);
+    dev_free(c->sun_clear_half);
+    c->S.bounds_half    = nullptr;
+    c->S.sun_clear_half = nullptr;
     c->n_slots = 0;
     c->have_volume = false;
     c->S.brick_words = nullptr;
@@ -215,6 +221,15 @@ static int update_sun_clear(vp_context* c)
     VP_CUDA(cudaDeviceSynchronize());
     S.sun_clear    = c->sun_clear;
     S.clear_margin = 0.25f * step;
+    S.sun_clear_half = nullptr;
+    if (c->bounds_half)
+    {
+        if (!c->sun_clear_half) VP_CUDA(cudaMalloc(&c->sun_clear_half, cells * sizeof(uint16_t)));
+        VP_CUDA(launch_pack_clear_half(c->sun_clear, c->sun_clear_half, cells, 0));
+        c->launches++;
+        VP_CUDA(cudaDeviceSynchronize());
+        S.sun_clear_half = c->sun_clear_half;
+    }
     return VP_OK;
 }
 
@@ -339,6 +354,26 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         cudaFree(tmp);
     }
 
+    // coarse cells = a volume too large for per-voxel windows: keep the per-cell tables L2-resident in half precision
+    // (VOLPATH_HALF_TABLES=0/1 overrides the choice, for measurements)
+    S.bounds_half = nullptr;
+    {
+        const char* ov   = getenv("VOLPATH_HALF_TABLES");
+        const bool  want = ov ? atoi(ov) != 0 : S.cell_log2 > 0;
+        if (c->bounds_cell && want)
+        {
+            const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
+            int *d_over = nullptr, h_over = 0;
+            VP_CUDA(cudaMalloc(&d_over, sizeof(int)));
+            VP_CUDA(cudaMemset(d_over, 0, sizeof(int)));
+            VP_CUDA(cudaMalloc(&c->bounds_half, cells * sizeof(uint32_t)));
+            VP_CUDA(launch_pack_bounds_half(c->bounds_cell, c->bounds_half, cells, d_over, 0));
+            VP_CUDA(cudaMemcpy(&h_over, d_over, sizeof(int), cudaMemcpyDeviceToHost));
+            cudaFree(d_over);
+            if (h_over) dev_free(c->bounds_half);  // values beyond the half range: stay with the float tables
+            S.bounds_half = c->bounds_half;
+        }
+    }
     S.brick_words  = c->words;
     S.stream_octets = c->octet_bytes > ((size_t)8 << 30) ? 1 : 0;  // pool >> 126 MB of L2: no reuse to protect
     S.brick_table  = c->table;

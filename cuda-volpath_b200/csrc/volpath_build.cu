@@ -430,6 +430,38 @@ cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// half-precision copies of the two per-cell tables for the production renderers (large volumes): every value is
+// rounded to the safe side -- max up (a vacuum jump, stored as a negative max, thereby toward zero), min down,
+// sun-clear up -- so the majorant stays a majorant and the vacuum shortcuts stay exact.  *overflow is set when a max
+// does not fit a half (the caller then keeps the float tables).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_bounds_half(const float2* __restrict__ b, uint32_t* __restrict__ out, size_t total, int* overflow)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const float2 v = b[i];
+        if (!(fabsf(v.x) < 60000.0f)) *overflow = 1;
+        __half2 h = __halves2half2(__float2half_ru(v.x), __float2half_rd(fmaxf(v.y, 0.0f)));
+        out[i]    = *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+__global__ void __launch_bounds__(256) k_pack_clear_half(const float* __restrict__ c, uint16_t* __restrict__ out, size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = __half_as_ushort(__float2half_ru(fminf(c[i], 60000.0f)));
+}
+cudaError_t launch_pack_bounds_half(const float2* bounds_cell, uint32_t* out, size_t total, int* d_overflow, cudaStream_t stream)
+{
+    k_pack_bounds_half<<<grid_for(total, 256), 256, 0, stream>>>(bounds_cell, out, total, d_overflow);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_clear_half(const float* sun_clear, uint16_t* out, size_t total, cudaStream_t stream)
+{
+    k_pack_clear_half<<<grid_for(total, 256), 256, 0, stream>>>(sun_clear, out, total);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // sun-clear distance: per bound cell, the distance along the sun direction after which only vacuum cells
 // (bound max == 0: no medium within D voxels) follow.  A shadow walk started anywhere in the cell can stop
 // there: every later tentative collision would see zero density (exact, not an approximation).

@@ -87,7 +87,20 @@ __device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
 // than the reference's per-voxel window (and identical to it when cell_log2 == 0).
 __device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
 {
-    return ldg_keep(S.bounds_cell + bound_cell_index(S, pos));
+    const uint32_t i = bound_cell_index(S, pos);
+    if (S.bounds_half)
+    {
+        const uint32_t w = ldg_keep(S.bounds_half + i);
+        return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    }
+    return ldg_keep(S.bounds_cell + i);
+}
+// distance from pos toward the sun after which only vacuum follows (plus the point-to-cell-centre margin)
+__device__ __forceinline__ float sun_clear_at(const Scene& S, float3 pos)
+{
+    const uint32_t i = bound_cell_index(S, pos);
+    if (S.sun_clear_half) return __half2float(__ushort_as_half(ldg_keep(S.sun_clear_half + i))) + S.clear_margin;
+    return ldg_keep(S.sun_clear + i) + S.clear_margin;
 }
 
 __device__ __forceinline__ float hg_eval_fast(float g, float c)

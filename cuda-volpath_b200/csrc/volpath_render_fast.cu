@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     dist = 0.0f;
                     lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
                     // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
-                    if (!JULIA && S.sun_clear) lim = fminf(lim, ldg_keep(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
+                    if (!JULIA && S.sun_clear) lim = fminf(lim, sun_clear_at(S, o));
                     st   = kModeStep | kShadow;
                 }
             }

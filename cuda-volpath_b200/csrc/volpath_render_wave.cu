@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                 while (dist < t_exit)
                 {
                     float  seg_end = JULIA ? t_exit : fminf(dist + kSearchRadius, t_exit);
-                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : ldg_keep(S.bounds_cell + bound_cell_index(S, o + s * dist));
+                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at(S, o + s * dist);
                     if (bnd.x <= 0.0f)
                     {
                         dist = fminf(dist + fmaxf(kSearchRadius, -bnd.x), t_exit);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                     float tn, tf;
                     box_slabs_fast(S, o, s, tn, tf);
                     float lim = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
-                    if (!JULIA && S.sun_clear) lim = fminf(lim, ldg_keep(S.sun_clear + bound_cell_index(S, o)) + S.clear_margin);
+                    if (!JULIA && S.sun_clear) lim = fminf(lim, sun_clear_at(S, o));
                     STF(F_INV, inv); STF(F_LIM, lim); STF(F_DIST, 0.0f); STF(F_PH, ph);
                     ST3(F_SX, s);
                     ST3(F_PX, pend);

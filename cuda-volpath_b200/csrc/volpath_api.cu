@@ -66,6 +66,7 @@ struct vp_context
     uint16_t* sun_clear_half = nullptr;
     float4*   env         = nullptr;
     std::vector<float> env_host;      // host copy of the env map (the CDF tables are built on the host, like init_envmap)
+    bool               env_host_stale = false;  // the device map was baked in place (vp_bake_sunsky) since the last copy
     float*    env_cdf_y   = nullptr;
     float*    env_cdf_x   = nullptr;
     bool      env_sampling = false;   // the reference's PASSIVE_ENVMAP 0 variant
@@ -174,6 +175,11 @@ static int update_env_sampling(vp_context* c)
     if (!c->env_sampling) return VP_OK;
     const int w = S.env_w, h = S.env_h;
     if (c->env_host.size() != (size_t)w * h * 4) return fail(VP_ERR_INVALID, "env sampling needs an environment map (init_envmap)");
+    if (c->env_host_stale)
+    {
+        VP_CUDA(cudaMemcpy(c->env_host.data(), c->env, c->env_host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        c->env_host_stale = false;
+    }
     const size_t       total = (size_t)w * h;
     std::vector<float> lum(total), cdf_x(total), cdf_y(h), row_sum(h);
     for (size_t i = 0; i < total; i++)
@@ -537,7 +543,40 @@ int vp_set_envmap(vp_context* c, const float* rgba, int width, int height)
     VP_CUDA(cudaMemcpy(c->env, rgba, (size_t)width * height * sizeof(float4), cudaMemcpyHostToDevice));
     c->S.env = c->env; c->S.env_w = width; c->S.env_h = height;
     c->env_host.assign(rgba, rgba + (size_t)width * height * 4);
+    c->env_host_stale = false;
     return update_env_sampling(c);
+}
+
+int vp_bake_sunsky(vp_context* c, const vp_sky_state* st, int width, int height)
+{
+    if (!c || !st || width < 1 || height < 2) return fail(VP_ERR_INVALID, "vp_bake_sunsky: bad arguments");
+    VP_CUDA(cudaSetDevice(c->device));
+    if (!c->env || c->S.env_w != width || c->S.env_h != height)
+    {
+        dev_free(c->env);
+        VP_CUDA(cudaMalloc(&c->env, (size_t)width * height * sizeof(float4)));
+    }
+    VP_CUDA(launch_bake_sunsky(*st, c->env, width, height, 0));
+    c->launches++;
+    c->S.env = c->env; c->S.env_w = width; c->S.env_h = height;
+    // the host copy is only needed by the CDF build of the env-sampling variant
+    c->env_host.resize((size_t)width * height * 4);
+    if (c->env_sampling)
+        VP_CUDA(cudaMemcpy(c->env_host.data(), c->env, c->env_host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    else
+        c->env_host_stale = true;
+    VP_CUDA(cudaDeviceSynchronize());
+    return update_env_sampling(c);
+}
+
+int vp_get_envmap(vp_context* c, float* h_out, int* wh2)
+{
+    if (!c || !wh2) return fail(VP_ERR_INVALID, "vp_get_envmap: bad arguments");
+    wh2[0] = c->S.env_w; wh2[1] = c->S.env_h;
+    if (!h_out || !c->env) return VP_OK;
+    VP_CUDA(cudaSetDevice(c->device));
+    VP_CUDA(cudaMemcpy(h_out, c->env, (size_t)c->S.env_w * c->S.env_h * sizeof(float4), cudaMemcpyDeviceToHost));
+    return VP_OK;
 }
 
 int vp_set_env_sampling(vp_context* c, int enable)
@@ -651,6 +690,18 @@ int vp_accumulate(vp_context* c, void* d_dst, const void* d_src, int size, vp_st
     VP_CUDA(cudaSetDevice(c->device));
     VP_CUDA(launch_accumulate((float4*)d_dst, (const float4*)d_src, size, (cudaStream_t)stream));
     c->launches++;
+    return VP_OK;
+}
+
+int vp_get_half_tables(vp_context* c, unsigned short* h_maxmin, unsigned short* h_clear, float* h_clear_f32, int* present)
+{
+    if (!c || !present) return fail(VP_ERR_INVALID, "vp_get_half_tables: bad arguments");
+    *present = c->bounds_half && c->sun_clear_half ? 1 : 0;
+    VP_CUDA(cudaSetDevice(c->device));
+    const size_t cells = (size_t)c->S.ncx * c->S.ncy * c->S.ncz;
+    if (*present && h_maxmin) VP_CUDA(cudaMemcpy(h_maxmin, c->bounds_half, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (*present && h_clear) VP_CUDA(cudaMemcpy(h_clear, c->sun_clear_half, cells * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (c->sun_clear && h_clear_f32) VP_CUDA(cudaMemcpy(h_clear_f32, c->sun_clear, cells * sizeof(float), cudaMemcpyDeviceToHost));
     return VP_OK;
 }
 

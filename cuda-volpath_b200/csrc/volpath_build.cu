@@ -641,4 +641,69 @@ cudaError_t launch_philox(uint32_t c0, uint32_t c1, uint32_t key, uint32_t* out2
     k_philox<<<1, 1, 0, stream>>>(c0, c1, key, out2);
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// sun/sky bake: one thread per texel of the lat-long map, the arithmetic of update_sunsky(baked = true)
+// (H.cpp:296-322): direction of the texel (must match Envmap::uv_to_dir), Skydome::skyColor (sky_tungsten.cpp:400-419:
+// theta, gamma in float; seven spectral samples of arhosekskymodel_radiance in double, ArHosekSkyModel.cpp:519-561,
+// 291-304; XYZ weights and XYZ -> RGB in float), times sunsky_scale; the lower half is the constant ground colour.
+// ---------------------------------------------------------------------------------------------------
+namespace
+{
+__device__ __forceinline__ double hosek_radiance(const double* __restrict__ c, double cos_theta, double gamma, double cos_gamma)
+{
+    const double expM   = exp(c[4] * gamma);
+    const double rayM   = cos_gamma * cos_gamma;
+    const double mieM   = (1.0 + cos_gamma * cos_gamma) / pow(1.0 + c[8] * c[8] - 2.0 * c[8] * cos_gamma, 1.5);
+    const double zenith = sqrt(cos_theta);
+    return (1.0 + c[0] * exp(c[1] / (cos_theta + 0.01))) * (c[2] + c[3] * expM + c[5] * rayM + c[6] * mieM + c[7] * zenith);
+}
+}  // namespace
+__global__ void __launch_bounds__(128) k_bake_sunsky(const __grid_constant__ vp_sky_state st, float4* __restrict__ env, int width, int height)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= width) return;
+    if (j >= height / 2)
+    {
+        env[(size_t)j * width + i] = make_float4(st.ground_rgb[0], st.ground_rgb[1], st.ground_rgb[2], 1.0f);
+        return;
+    }
+    const float  phi   = (float)((double)((float)i / width * 2) * 3.14159265358979323846);
+    const float  theta = (float)((double)((float)j / height) * 3.14159265358979323846);
+    const float3 d     = f3(sinf(theta) * sinf(phi), cosf(theta), sinf(theta) * -cosf(phi));
+    const float  th    = acosf(d.y);
+    const float  dt    = d.x * st.sun_dir[0] + d.y * st.sun_dir[1] + d.z * st.sun_dir[2];
+    const float  gm    = fminf(fmaxf(acosf(fminf(fmaxf(dt, -1.0f), 1.0f)) * st.gamma_scale, 0.0f), 3.14159265358979323846f);
+    const double cth = cos((double)th), cgm = cos((double)gm);
+    float3       xyz = f3(0.0f);
+    for (int k = 0; k < 7; k++)
+    {
+        const double wl  = st.lambdas[k];
+        const int    low = (int)((wl - 320.0) / 40.0);
+        double       r   = 0.0;
+        if (low >= 0 && low < 11)
+        {
+            const double interp = fmod((wl - 320.0) / 40.0, 1.0);
+            r = hosek_radiance(st.configs[low], cth, gm, cgm) * st.radiances[low] * st.emission_correction_factor_sky[low];
+            if (!(interp < 1e-6))
+            {
+                r *= 1.0 - interp;
+                if (low + 1 < 11)
+                    r += interp * hosek_radiance(st.configs[low + 1], cth, gm, cgm) * st.radiances[low + 1] * st.emission_correction_factor_sky[low + 1];
+            }
+        }
+        const float rf = (float)r;
+        xyz = xyz + f3(st.weights[k][0], st.weights[k][1], st.weights[k][2]) * rf;
+    }
+    const float3 c = f3(3.240479f * xyz.x + -1.537150f * xyz.y + -0.498535f * xyz.z,
+                        -0.969256f * xyz.x + 1.875991f * xyz.y + 0.041556f * xyz.z,
+                        0.055648f * xyz.x + -0.204043f * xyz.y + 1.057311f * xyz.z);
+    env[(size_t)j * width + i] = make_float4(c.x * st.sunsky_scale, c.y * st.sunsky_scale, c.z * st.sunsky_scale, st.sunsky_scale);
+}
+cudaError_t launch_bake_sunsky(const vp_sky_state& st, float4* env, int width, int height, cudaStream_t stream)
+{
+    dim3 grid((width + 127) / 128, height);
+    k_bake_sunsky<<<grid, 128, 0, stream>>>(st, env, width, height);
+    return cudaGetLastError();
+}
 }  // namespace vp

@@ -45,6 +45,7 @@ cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick
 cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, int margin,
                                 float cell_world, cudaStream_t stream);
 cudaError_t launch_sun_clear(const Scene& S, float3 sun, float step, float* out, cudaStream_t stream);
+cudaError_t launch_bake_sunsky(const vp_sky_state& st, float4* env, int width, int height, cudaStream_t stream);
 cudaError_t launch_pack_bounds_half(const float2* bounds_cell, uint32_t* out, size_t total, int* d_overflow, cudaStream_t stream);
 cudaError_t launch_pack_clear_half(const float* sun_clear, uint16_t* out, size_t total, cudaStream_t stream);
 cudaError_t launch_expand_cell_bounds(const Scene& S, float2* bounds_voxel, cudaStream_t stream);

@@ -27,6 +27,14 @@ class Float3(ctypes.Structure):
     _fields_ = [("x", ctypes.c_float), ("y", ctypes.c_float), ("z", ctypes.c_float)]
 
 
+class SkyState(ctypes.Structure):
+    """vp_sky_state (include/volpath.h): the host-side state of the reference's Skydome after prepareForRender()."""
+    _fields_ = [("configs", ctypes.c_double * 9 * 11), ("radiances", ctypes.c_double * 11),
+                ("emission_correction_factor_sky", ctypes.c_double * 11), ("lambdas", ctypes.c_float * 7),
+                ("weights", ctypes.c_float * 3 * 7), ("gamma_scale", ctypes.c_float), ("sun_dir", ctypes.c_float * 3),
+                ("ground_rgb", ctypes.c_float * 3), ("sunsky_scale", ctypes.c_float)]
+
+
 class Dim3(ctypes.Structure):
     _fields_ = [("x", c_uint), ("y", c_uint), ("z", c_uint)]
 
@@ -50,6 +58,8 @@ SIGNATURES = {
     "vp_set_envmap": (c_int, [c_vp, c_fp, c_int, c_int]),
     "vp_set_sun": (c_int, [c_vp, c_fp, c_fp]),
     "vp_set_env_sampling": (c_int, [c_vp, c_int]),
+    "vp_bake_sunsky": (c_int, [c_vp, c_vp, c_int, c_int]),
+    "vp_get_envmap": (c_int, [c_vp, c_fp, ctypes.POINTER(c_int)]),
     "vp_set_inv_view": (c_int, [c_vp, c_fp]),
     "vp_precompute_opacity": (c_int, [c_vp, c_fp]),
     "vp_free_volume": (c_int, [c_vp]),
@@ -60,6 +70,7 @@ SIGNATURES = {
     "vp_sync": (c_int, [c_vp]),
     "vp_get_bounds_voxel": (c_int, [c_vp, c_fp]),
     "vp_get_bounds_cell": (c_int, [c_vp, c_fp, ctypes.POINTER(c_int)]),
+    "vp_get_half_tables": (c_int, [c_vp, c_vp, c_vp, c_fp, ctypes.POINTER(c_int)]),
     "vp_get_opacity": (c_int, [c_vp, c_fp]),
     "vp_fetch_density": (c_int, [c_vp, c_fp, c_int, c_int, c_fp]),
     "vp_volume_stats": (c_int, [c_vp, c_u64p]),

@@ -134,6 +134,52 @@ class Renderer:
         _l.check(self.L.vp_get_bounds_cell(self.h, _fp(out), d))
         return out
 
+    def bake_sunsky(self, state, width=1024, height=512, sunsky_scale=0.02, ground_albedo=0.01, gamma_scale=1.0):
+        """update_sunsky(baked = true)'s per-texel loop + init_envmap in one device kernel (volumeRender.cpp:296-325);
+        `state`: dict as sunsky.default_sky_state() / tests/golden/sunsky_states.npz (configs, radiances, ecf_sky,
+        lambdas, weights, sun_dir, sun_power).  The sun itself still goes through set_sun."""
+        from .sunsky import ground_radiance
+
+        st = _l.SkyState()
+        cfg = np.asarray(state["configs"], np.float64).reshape(11, 9)
+        for w in range(11):
+            for k in range(9):
+                st.configs[w][k] = cfg[w, k]
+            st.radiances[w] = float(state["radiances"][w])
+            st.emission_correction_factor_sky[w] = float(state["ecf_sky"][w])
+        for i in range(7):
+            st.lambdas[i] = float(state["lambdas"][i])
+            for ch in range(3):
+                st.weights[i][ch] = float(state["weights"][i][ch])
+        st.gamma_scale = gamma_scale
+        g = ground_radiance(state["sun_dir"], state["sun_power"], ground_albedo)
+        for ch in range(3):
+            st.sun_dir[ch] = float(state["sun_dir"][ch])
+            st.ground_rgb[ch] = float(g[ch])
+        st.sunsky_scale = sunsky_scale
+        _l.check(self.L.vp_bake_sunsky(self.h, ctypes.byref(st), width, height))
+
+    def envmap(self):
+        d = (ctypes.c_int * 2)()
+        _l.check(self.L.vp_get_envmap(self.h, None, d))
+        out = np.empty((d[1], d[0], 4), np.float32)
+        _l.check(self.L.vp_get_envmap(self.h, _fp(out), d))
+        return out
+
+    def half_tables(self):
+        """The half-precision per-cell tables of the production renderers (large volumes): ((max, min) as float16
+        [cz][cy][cx][2] with the vacuum jumps still encoded, sun-clear float16 [cz][cy][cx], sun-clear float32), or None
+        while the float tables are in use."""
+        d = (ctypes.c_int * 3)()
+        _l.check(self.L.vp_get_bounds_cell(self.h, None, d))
+        mm = np.empty((d[2], d[1], d[0], 2), np.float16)
+        cl = np.empty((d[2], d[1], d[0]), np.float16)
+        cf = np.empty((d[2], d[1], d[0]), np.float32)
+        present = ctypes.c_int(0)
+        _l.check(self.L.vp_get_half_tables(self.h, mm.ctypes.data_as(ctypes.c_void_p), cl.ctypes.data_as(ctypes.c_void_p), _fp(cf),
+                                           ctypes.byref(present)))
+        return (mm, cl, cf) if present.value else None
+
     def opacity(self):
         nx, ny, nz = self.dims
         out = np.empty((nz, ny, nx), np.float32)

@@ -23,6 +23,22 @@ def default_sunsky():
     return env, z["sun_dir"].astype(np.float32), z["sun_power"].astype(np.float32)
 
 
+def default_sky_state():
+    """The host-side state behind default_sunsky() (what the reference's Skydome holds after prepareForRender() for
+    setup_sunsky(0.5, 0.2)): the input of Renderer.bake_sunsky, which evaluates the map on the device."""
+    z = np.load(_DATA)
+    st = {k[len("state_"):]: z[k] for k in z.files if k.startswith("state_")}
+    st["sun_dir"] = z["sun_dir"].astype(np.float32)
+    st["sun_power"] = z["sun_power"].astype(np.float32)
+    return st
+
+
+def ground_radiance(sun_dir, sun_power, ground_albedo=0.01):
+    """Lower half of the baked map: ground_albedo * sun_dir.y * sun_power * (pi (0.45 / 94)^2), volumeRender.cpp:315-320."""
+    k = np.pi * (0.45 / np.float32(94.0) * 0.45 / np.float32(94.0))
+    return ((np.float32(ground_albedo) * np.float32(sun_dir[1]) * np.asarray(sun_power, np.float32)).astype(np.float32) * k).astype(np.float32)
+
+
 def constant_sky(rgb=(0.03, 0.07, 0.23), ground=(0.03, 0.03, 0.03), width=16, height=8):
     """The reference's tiny two-colour test map (volumeRender.cpp:1372-1385)."""
     env = np.empty((height, width, 4), np.float32)

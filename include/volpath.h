@@ -103,6 +103,26 @@ int vp_set_julia(vp_context* ctx);
 int vp_set_filter(vp_context* ctx, int linear);                                   /* set_texture_filter_mode */
 int vp_set_envmap(vp_context* ctx, const float* rgba, int width, int height);     /* init_envmap, host ptr */
 int vp_set_sun(vp_context* ctx, const float* dir3, const float* power3);          /* set_sun */
+/* Sun/sky bake on the device: the per-texel loop of update_sunsky(baked = true) (volumeRender.cpp:296-322) --
+ * Skydome::skyColor (sunsky/sky_tungsten.cpp:400-419) over arhosekskymodel_radiance (sunsky/hosek/ArHosekSkyModel.cpp:
+ * 519-561) -- evaluated by one kernel straight into the context's environment map (replaces the host loop + init_envmap;
+ * no 8 MB upload per sun change).  The caller passes the small host-side state the reference holds after
+ * Skydome::prepareForRender(): the cooked Hosek configurations stay host code. */
+typedef struct vp_sky_state
+{
+    double configs[11][9];                      /* ArHosekSkyModelState::configs */
+    double radiances[11];                       /* ::radiances */
+    double emission_correction_factor_sky[11];  /* ::emission_correction_factor_sky */
+    float  lambdas[7];                          /* Spectral::spectralXyzWeights, the NumSamplesValid = 7 used ones */
+    float  weights[7][3];
+    float  gamma_scale;                         /* Skydome::_gammaScale (1) */
+    float  sun_dir[3];                          /* Skydome::sunDirection() */
+    float  ground_rgb[3];                       /* lower half: ground_albedo * sun_dir.y * sun_power * pi (0.45/94)^2 */
+    float  sunsky_scale;                        /* 0.02 (volumeRender.cpp:292) */
+} vp_sky_state;
+int vp_bake_sunsky(vp_context* ctx, const vp_sky_state* state, int width, int height);
+int vp_get_envmap(vp_context* ctx, float* h_out_rgba, int* wh2);  /* introspection: the environment map in use */
+
 /* the reference's PASSIVE_ENVMAP switch (K.cu:21), a compile-time macro there: 0 (default, as shipped) = the environment
  * is picked up by escaping paths; enable != 0 = env-map importance sampling + one-sample MIS with phase sampling at
  * every scatter event (K.cu:904-1034, 2220-2297); the CDF tables are built like init_envmap builds them */
@@ -132,6 +152,10 @@ int vp_sync(vp_context* ctx);
 /* introspection for tests / benchmarks */
 int vp_get_bounds_voxel(vp_context* ctx, float* h_out_maxmin);   /* [nz][ny][nx][2], (max,min) */
 int vp_get_bounds_cell(vp_context* ctx, float* h_out_maxmin, int* dims3); /* [cz][cy][cx][2] */
+/* half-precision copies of the per-cell tables the production renderers read on large volumes: (max,min) as two
+ * IEEE halves per cell and the sun-clear distance as one; *present = 0 when the float tables are in use */
+int vp_get_half_tables(vp_context* ctx, unsigned short* h_out_maxmin, unsigned short* h_out_clear, float* h_out_clear_f32,
+                       int* present);
 int vp_get_opacity(vp_context* ctx, float* h_out);               /* [nz][ny][nx], 0 where not stored */
 int vp_fetch_density(vp_context* ctx, const float* h_pos3, int n, int parity_filter, float* h_out); /* world pos */
 int vp_volume_stats(vp_context* ctx, unsigned long long* out8);  /* bricks, nonempty bricks, bytes ... */

@@ -8,6 +8,9 @@
 
 #include "vecmath.h"
 #include "sunsky/sunsky.h"
+#include "sunsky/hosek/ArHosekSkyModel.h"
+
+namespace Tungsten { namespace Spectral { void spectralXyzWeights(int samples, float lambdas[], Vec3f weights[]); } }
 
 extern "C" int ref_bake_sunsky(float x, float y, int hdrwidth, int hdrheight, float* rgba_out, float* sun_dir3,
                                float* sun_power3)
@@ -45,5 +48,38 @@ extern "C" int ref_bake_sunsky(float x, float y, int hdrwidth, int hdrheight, fl
     }
     sun_dir3[0] = sun_dir.x; sun_dir3[1] = sun_dir.y; sun_dir3[2] = sun_dir.z;
     sun_power3[0] = sun_power.x; sun_power3[1] = sun_power.y; sun_power3[2] = sun_power.z;
+    return 0;
+}
+
+// The state the reference's host holds after Skydome::prepareForRender() (sky_tungsten.cpp:377-398) for the sun
+// position (x, y) of setup_sunsky: the cooked Hosek configurations of the 11 spectral bands, their radiances and
+// emission corrections, and the spectral XYZ weights / wavelengths.  This is the INPUT of the GPU sky bake
+// (vp_bake_sunsky); the per-texel evaluation above is what that kernel replaces.
+extern "C" int ref_sky_state(float x, float y, double* configs99, double* radiances11, double* ecf_sky11, float* lambdas10,
+                             float* weights30, float* sun_dir3, float* sun_power3)
+{
+    SkyModel<Tungsten::Skydome> s;
+    y *= 0.5f;
+    y = fminf(fmaxf(y, 0.0f), 0.49999f);
+    s.setSunPhi(x * M_PI * 2);
+    s.setSunTheta(y * M_PI);
+    Tungsten::Skydome dome;  // constructor defaults: temperature 5777, gamma scale 1, turbidity 2, intensity 100
+    float3 sun          = s.getSunDir();
+    float  sunElevation = std::asin(fminf(fmaxf(sun.y, -1.0f), 1.0f));
+    ArHosekSkyModelState* st =
+        arhosekskymodelstate_alienworld_alloc_init(sunElevation, dome.intensity(), 5777.0f, dome.turbidity(), 0.2f);
+    for (int w = 0; w < 11; w++)
+    {
+        for (int k = 0; k < 9; k++) configs99[w * 9 + k] = st->configs[w][k];
+        radiances11[w] = st->radiances[w];
+        ecf_sky11[w]   = st->emission_correction_factor_sky[w];
+    }
+    arhosekskymodelstate_free(st);
+    float3 wts[10];
+    Tungsten::Spectral::spectralXyzWeights(10, lambdas10, wts);
+    for (int i = 0; i < 10; i++) { weights30[3 * i] = wts[i].x; weights30[3 * i + 1] = wts[i].y; weights30[3 * i + 2] = wts[i].z; }
+    float3 sp = s.sunColor() * 0.02f;
+    sun_dir3[0] = sun.x; sun_dir3[1] = sun.y; sun_dir3[2] = sun.z;
+    sun_power3[0] = sp.x; sun_power3[1] = sp.y; sun_power3[2] = sp.z;
     return 0;
 }

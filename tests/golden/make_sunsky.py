@@ -17,6 +17,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
+def sky_state(lib, x, y):
+    """The host-side state behind one sun position (oracle/ref_sunsky_driver.cpp: ref_sky_state) -- the input of the
+    GPU sky bake (vp_bake_sunsky)."""
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    cfg, rad, ecf = np.zeros((11, 9)), np.zeros(11), np.zeros(11)
+    lam, wts = np.zeros(10, np.float32), np.zeros((10, 3), np.float32)
+    sd, sp = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    lib.ref_sky_state.argtypes = [ctypes.c_float, ctypes.c_float, dp, dp, dp, fp, fp, fp, fp]
+    lib.ref_sky_state(x, y, cfg.ctypes.data_as(dp), rad.ctypes.data_as(dp), ecf.ctypes.data_as(dp), lam.ctypes.data_as(fp),
+                      wts.ctypes.data_as(fp), sd.ctypes.data_as(fp), sp.ctypes.data_as(fp))
+    return dict(configs=cfg, radiances=rad, ecf_sky=ecf, lambdas=lam, weights=wts, sun_dir=sd, sun_power=sp)
+
+
 def main():
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libvolpath_ref_sunsky.so"))
     W, H = 1024, 512
@@ -33,7 +46,22 @@ def main():
     assert np.all(img[: H // 2, :, 3] == np.float32(0.02))
     out = os.path.join(ROOT, "cuda-volpath_b200", "data", "sunsky_default.npz")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    np.savez_compressed(out, sky=sky, ground=ground, sun_dir=sd, sun_power=sp, width=W, height=H)
+    st = sky_state(lib, 0.5, 0.2)
+    assert np.array_equal(st["sun_dir"], sd) and np.array_equal(st["sun_power"], sp)
+    np.savez_compressed(out, sky=sky, ground=ground, sun_dir=sd, sun_power=sp, width=W, height=H,
+                        **{"state_" + k: v for k, v in st.items() if k not in ("sun_dir", "sun_power")})
+    # golden vectors for the sky bake (oracle/sky_oracle.py, k_bake_sunsky): state in, the reference's own map out
+    gold = {}
+    for tag, (x, y, w, h) in {"default": (0.5, 0.2, 128, 64), "low": (0.3, 0.9, 96, 48), "zenith": (0.8, 0.02, 64, 32)}.items():
+        im = np.zeros((h, w, 4), np.float32)
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        lib.ref_bake_sunsky(x, y, w, h, im.ctypes.data_as(fp), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
+        for k, v in sky_state(lib, x, y).items():
+            gold[tag + "_" + k] = v
+        gold[tag + "_env"] = im
+    g = os.path.join(HERE, "sunsky_states.npz")
+    np.savez_compressed(g, **gold)
+    print(g, os.path.getsize(g))
     print("sun_dir", sd, "sun_power", sp, "ground", ground, "sky range", sky.min(), sky.max())
     print(out, os.path.getsize(out))
 

@@ -5,12 +5,15 @@
 Nothing here reads /root/reference."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 
 from conftest import SUN_DIR, SUN_POWER, param_from_bytes, setup_renderer, setup_scene
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -396,6 +399,36 @@ def test_fast_renderer_julia_statistical_parity(R, vp):
     assert abs(f[..., :3].mean() - a[..., :3].mean()) <= 0.02 * a[..., :3].mean()
 
 
+def test_half_precision_cell_tables_round_to_the_safe_side(R, oracle, vp, monkeypatch):
+    """Large volumes keep the two per-cell tables of the production renderers in half precision so that they stay
+    L2-resident: max (and the negative vacuum jumps) rounded up, min down, sun-clear up -- never the other way -- and
+    the renders agree with the float tables (same paths except where a majorant moved by its last half bit)."""
+    vol = small_cloud(oracle, (96, 64, 80), seed=3)
+    monkeypatch.setenv("VOLPATH_FORCE_CELL_LOG2", "1")
+    monkeypatch.setenv("VOLPATH_HALF_TABLES", "0")
+    setup_renderer(R, vp, vol, False, True)
+    assert R.half_tables() is None
+    P = vp.default_param(96, 64)
+    P.density = 300.0
+    a = R.render(P, 0, 16, mode=vp.MODE_FAST)
+    monkeypatch.setenv("VOLPATH_HALF_TABLES", "1")
+    setup_renderer(R, vp, vol, False, True)
+    mm, cl, cf = R.half_tables()
+    raw = R.bounds_cell(raw_jumps=True)
+    assert (mm[..., 0].astype(np.float32) >= raw[..., 0]).all()  # max up, jumps (negative) toward zero
+    assert (mm[..., 1].astype(np.float32) <= raw[..., 1]).all() and (mm[..., 1] >= 0).all()
+    assert ((mm[..., 0] > 0) == (raw[..., 0] > 0)).all()          # a cell stays vacuum / medium
+    assert (cl.astype(np.float32) >= cf).all()
+    assert np.allclose(mm.astype(np.float32), raw, rtol=1e-3, atol=1e-7) and np.allclose(cl.astype(np.float32), cf, rtol=1e-3, atol=1e-7)
+    b = R.render(P, 0, 16, mode=vp.MODE_FAST)
+    same = (a[..., 3] == b[..., 3]).mean()
+    assert same > 0.9, same
+    # the paths that did change are fresh samples: judge the means against the paired per-pixel noise (4 sigma)
+    for x, y in ((a[..., 3], b[..., 3]), (a[..., :3].sum(-1), b[..., :3].sum(-1))):
+        d = (x - y).astype(np.float64)
+        assert abs(d.mean()) <= 4.0 * d.std() / np.sqrt(d.size) + 1e-3 * x.mean(), (d.mean(), d.std(), x.mean())
+
+
 def test_fast_renderer_frame_sharding_is_exact_in_scatter_counts(R, oracle, vp):
     """Multi-GPU contract on one GPU: the union of the strided frame subsets is the full frame set; .w (integer
     scatter counts) is identical under any partition, rgb agrees up to fp32 summation order."""
@@ -539,3 +572,42 @@ def _ref_cuda_mis():
     if not have_ref("libvolpath_ref_cuda_mis.so"):
         pytest.skip("oracle/_ref/libvolpath_ref_cuda_mis.so not built")
     return RefCuda(mis=True)
+
+
+@pytest.mark.parametrize("tag", ["default", "low", "zenith"])
+def test_sky_bake_on_device_vs_reference_bake(R, vp, tag):
+    """vp_bake_sunsky: the device evaluates the map the reference's host loop bakes
+    (volumeRender.cpp:296-322) from the same host-side Hosek state; <= 1e-5 relative to the reference's own output."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sunsky_states.npz"))
+    st = {k: g[tag + "_" + k] for k in ("configs", "radiances", "ecf_sky", "lambdas", "weights", "sun_dir", "sun_power")}
+    want = g[tag + "_env"]
+    h, w = want.shape[:2]
+    R.bake_sunsky(st, w, h)
+    got = R.envmap()
+    assert got.shape == want.shape and np.all(np.isfinite(got))
+    assert np.array_equal(got[h // 2:], want[h // 2:]) and np.array_equal(got[..., 3], want[..., 3])
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
+    assert rel.max() <= 1e-5, rel.max()
+
+
+def test_sky_bake_default_equals_the_shipped_fixture_and_renders_the_same(R, oracle, vp):
+    """The default sun/sky baked on the device equals the fixture baked by the reference's host code, and a render
+    with it equals a render with the uploaded fixture up to the 1e-5 of the map."""
+    env, sd, sp = vp.default_sunsky()
+    vol = small_cloud(oracle, (48, 32, 56))
+    setup_renderer(R, vp, vol, False, True, env=env)
+    R.set_sun(sd, sp)
+    P = vp.default_param(64, 48)
+    P.density = 200.0
+    a = R.render(P, 0, 8, mode=vp.MODE_FAST)
+    R.bake_sunsky(vp.default_sky_state())
+    got = R.envmap()
+    assert got.shape == env.shape
+    rel = np.abs(got - env) / np.maximum(np.abs(env), 1e-6)
+    # <= 1e-5 relative; the last rows above the horizon (cos(theta) + 0.01 < 0.05 inside an exponential) amplify the
+    # 1-ulp differences between device and host cosf / acosf: <= 2e-4 there
+    h = env.shape[0]
+    assert rel[: h // 2 - 8].max() <= 1e-5 and rel.max() <= 2e-4, (rel[: h // 2 - 8].max(), rel.max())
+    b = R.render(P, 0, 8, mode=vp.MODE_FAST)
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert np.allclose(a[..., :3], b[..., :3], rtol=1e-4, atol=1e-6)

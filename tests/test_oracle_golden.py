@@ -1,10 +1,14 @@
 """CPU: the oracle (oracle/volpath_oracle.cpp) against golden vectors generated from the REFERENCE ITSELF
 (tests/golden/make_golden.py, reference kernel source compiled by g++).  Bit-exact: both sides are CPU builds with
 no FMA contraction and the same libm."""
+import os
+
 import numpy as np
 import pytest
 
 from conftest import SUN_DIR, param_from_bytes, setup_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_hash_and_rng_streams(oracle, golden):
@@ -130,3 +134,24 @@ def test_env_importance_sampling_mis_variant_bit_for_bit(golden, vp, name, pkey)
     o.set_env_sampling(False)
     assert not np.array_equal(o.render(P, 0, 3), want)
     o.close()
+
+
+@pytest.mark.parametrize("tag", ["default", "low", "zenith"])
+def test_sky_bake_restatement_vs_reference_bake(tag):
+    """oracle/sky_oracle.py (the per-texel loop of update_sunsky + Skydome::skyColor + the Hosek spectral radiance)
+    against maps baked by the reference's own code (tests/golden/make_sunsky.py): <= 5e-6 relative (float vs double
+    libm differences), ground half and alpha exact."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sky_oracle
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sunsky_states.npz"))
+    st = {k: g[tag + "_" + k] for k in ("configs", "radiances", "ecf_sky", "lambdas", "weights", "sun_dir", "sun_power")}
+    want = g[tag + "_env"]
+    h, w = want.shape[:2]
+    got = sky_oracle.bake_sunsky(st, w, h)
+    assert np.array_equal(got[h // 2:], want[h // 2:]) and np.array_equal(got[..., 3], want[..., 3])
+    assert np.all(np.isfinite(got))
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
+    assert rel.max() <= 5e-6, rel.max()

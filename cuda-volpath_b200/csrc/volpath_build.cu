@@ -144,9 +144,90 @@ __global__ void __launch_bounds__(256) k_bounds_axis(const TIn* __restrict__ in,
         out[idx] = r;
     }
 }
+// First sweep (x axis, dense float input -- the only one that reads the full-resolution volume): rows are contiguous, so a
+// CTA STAGES a row segment in shared memory with coalesced loads, reduces it once to (max, min) per aligned block of 8
+// voxels, and every output cell then combines whole blocks plus at most 7 + 7 single voxels at the window ends: C2
+// (window 108 voxels per cell of 8): 17 shared-memory reads per output instead of 108 global ones.  Comparisons only:
+// the result is the same bits as the plain loop above / H.cpp:1089-1267.
+constexpr int kRowBlock = 8;
+__global__ void __launch_bounds__(256) k_bounds_x_smem(const float* __restrict__ in, float2* __restrict__ out, int nx, size_t rows, int D,
+                                                        int cell, int cells_per_seg, int span_max)
+{
+    extern __shared__ float sm[];                                        // [span_max] voxels
+    float2*   bl   = reinterpret_cast<float2*>(sm + span_max);          // [span_max / 8 + 1] block bounds
+    const int m    = (nx + cell - 1) / cell;
+    const int segs = (m + cells_per_seg - 1) / cells_per_seg;
+    for (size_t w = blockIdx.x; w < rows * (size_t)segs; w += gridDim.x)
+    {
+        const size_t row = w / segs;
+        const int    c0 = (int)(w % segs) * cells_per_seg, c1 = min(m, c0 + cells_per_seg);
+        const int    lo = (max(0, c0 * cell - D) / kRowBlock) * kRowBlock;
+        const int    hi = min(nx - 1, (c1 - 1) * cell + cell - 1 + D);
+        const int    span = hi - lo + 1, nb = (span + kRowBlock - 1) / kRowBlock;
+        const float* src  = in + row * (size_t)nx + lo;
+        for (int t = threadIdx.x; t < span; t += blockDim.x) sm[t] = src[t];
+        __syncthreads();
+        for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        {
+            const int e  = min(span, b * kRowBlock + kRowBlock);
+            float     mx = sm[b * kRowBlock], mn = mx;
+            for (int t = b * kRowBlock + 1; t < e; t++)
+            {
+                const float v = sm[t];
+                mx = v > mx ? v : mx;
+                mn = v < mn ? v : mn;
+            }
+            bl[b] = make_float2(mx, mn);
+        }
+        __syncthreads();
+        for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
+        {
+            int       t = max(0, c * cell - D) - lo;
+            const int e = min(nx - 1, c * cell + cell - 1 + D) - lo;  // inclusive
+            float     mx = sm[t], mn = mx;
+            for (t++; t <= e && (t & (kRowBlock - 1)); t++)
+            {
+                const float v = sm[t];
+                mx = v > mx ? v : mx;
+                mn = v < mn ? v : mn;
+            }
+            for (; t + kRowBlock - 1 <= e; t += kRowBlock)
+            {
+                const float2 q = bl[t / kRowBlock];
+                mx = q.x > mx ? q.x : mx;
+                mn = q.y < mn ? q.y : mn;
+            }
+            for (; t <= e; t++)
+            {
+                const float v = sm[t];
+                mx = v > mx ? v : mx;
+                mn = v < mn ? v : mn;
+            }
+            out[row * (size_t)m + c] = make_float2(mx, mn);
+        }
+        __syncthreads();
+    }
+}
 cudaError_t launch_bounds_axis_f32(const float* in, float2* out, int n0, int n1, int n2, int axis, int D, int cell,
                                    cudaStream_t stream)
 {
+    if (axis == 0 && !getenv("VOLPATH_BOUNDS_PLAIN"))
+    {
+        // segment = as many cells as fit 8192 staged voxels (32 KB + 8 KB of block bounds: 5 CTAs per SM)
+        const int span_max = 8192;
+        int       cps      = (span_max - 2 * D - 2 * kRowBlock) / cell;
+        if (cps >= 1)
+        {
+            const int    m    = (n0 + cell - 1) / cell;
+            if (cps > m) cps = m;
+            const size_t rows = (size_t)n1 * n2, work = rows * (size_t)((m + cps - 1) / cps);
+            const int    span = (cps * cell + 2 * D + 2 * kRowBlock + 3) & ~3;  // what a segment can span at most
+            const size_t smem = (size_t)span * sizeof(float) + ((size_t)span / kRowBlock + 2) * sizeof(float2);
+            const unsigned grid = (unsigned)(work < (size_t)148 * 16 ? work : (size_t)148 * 16);
+            k_bounds_x_smem<<<grid, 256, smem, stream>>>(in, out, n0, rows, D, cell, cps, span);
+            return cudaGetLastError();
+        }
+    }
     int    na    = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
     size_t total = (size_t)n0 * n1 * n2 / na * ((na + cell - 1) / cell);
     k_bounds_axis<float><<<grid_for(total, 256, (size_t)148 * 256), 256, 0, stream>>>(in, out, n0, n1, n2, axis, D, cell);
@@ -672,7 +753,9 @@ __global__ void __launch_bounds__(128) k_bake_sunsky(const __grid_constant__ vp_
     const float  theta = (float)((double)((float)j / height) * 3.14159265358979323846);
     const float3 d     = f3(sinf(theta) * sinf(phi), cosf(theta), sinf(theta) * -cosf(phi));
     const float  th    = acosf(d.y);
-    const float  dt    = d.x * st.sun_dir[0] + d.y * st.sun_dir[1] + d.z * st.sun_dir[2];
+    // float arithmetic in the host's operation order, without FMA contraction (the reference's host build has none): near
+    // the sun acos() turns one ulp of this dot product into 1e-4 of gamma
+    const float  dt    = __fadd_rn(__fadd_rn(__fmul_rn(d.x, st.sun_dir[0]), __fmul_rn(d.y, st.sun_dir[1])), __fmul_rn(d.z, st.sun_dir[2]));
     const float  gm    = fminf(fmaxf(acosf(fminf(fmaxf(dt, -1.0f), 1.0f)) * st.gamma_scale, 0.0f), 3.14159265358979323846f);
     const double cth = cos((double)th), cgm = cos((double)gm);
     float3       xyz = f3(0.0f);
@@ -693,11 +776,13 @@ __global__ void __launch_bounds__(128) k_bake_sunsky(const __grid_constant__ vp_
             }
         }
         const float rf = (float)r;
-        xyz = xyz + f3(st.weights[k][0], st.weights[k][1], st.weights[k][2]) * rf;
+        xyz = f3(__fadd_rn(xyz.x, __fmul_rn(st.weights[k][0], rf)), __fadd_rn(xyz.y, __fmul_rn(st.weights[k][1], rf)),
+                 __fadd_rn(xyz.z, __fmul_rn(st.weights[k][2], rf)));
     }
-    const float3 c = f3(3.240479f * xyz.x + -1.537150f * xyz.y + -0.498535f * xyz.z,
-                        -0.969256f * xyz.x + 1.875991f * xyz.y + 0.041556f * xyz.z,
-                        0.055648f * xyz.x + -0.204043f * xyz.y + 1.057311f * xyz.z);
+    auto row = [&](float a, float b, float c3) {
+        return __fadd_rn(__fadd_rn(__fmul_rn(a, xyz.x), __fmul_rn(b, xyz.y)), __fmul_rn(c3, xyz.z));
+    };
+    const float3 c = f3(row(3.240479f, -1.537150f, -0.498535f), row(-0.969256f, 1.875991f, 0.041556f), row(0.055648f, -0.204043f, 1.057311f));
     env[(size_t)j * width + i] = make_float4(c.x * st.sunsky_scale, c.y * st.sunsky_scale, c.z * st.sunsky_scale, st.sunsky_scale);
 }
 cudaError_t launch_bake_sunsky(const vp_sky_state& st, float4* env, int width, int height, cudaStream_t stream)

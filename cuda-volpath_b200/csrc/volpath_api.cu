@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "volpath_common.cuh"
@@ -80,7 +81,16 @@ struct vp_context
     bool      have_volume = false;
     // instrumentation
     unsigned long long* d_stats = nullptr;
-    unsigned long long* d_work  = nullptr;  // work-pool counter of the fast renderer
+    // work-pool counters of the production renderers, one per launch in flight: slots 0..7 belong to the overlap ring of
+    // the render_kernel shim (below), 8..11 rotate over launches on caller-given streams
+    unsigned long long* d_work  = nullptr;
+    unsigned            work_rr = 0;
+    // render_kernel shim, VP_MODE_FAST: consecutive one-frame launches go round-robin to four internal BLOCKING streams, so
+    // the long tail of frame n (its last few paths) overlaps the bulk of frame n + 1 whenever the host does not
+    // synchronise in between; blocking streams keep the legacy default-stream ordering the reference host relies on
+    // (its copies, scale / gamma_correct and synchronisations still wait for every frame).  VOLPATH_SHIM_OVERLAP=0: off
+    cudaStream_t        ring[8] = {};  // VOLPATH_SHIM_STREAMS of them in use (default 4)
+    unsigned            ring_rr = 0;
     bool                stats_on = false;
     unsigned long long  launches = 0;
     cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
@@ -421,7 +431,7 @@ int vp_create(int device, vp_context** out)
     memcpy(c->inv_model, id, sizeof(id));
     VP_CUDA(cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));
     VP_CUDA(cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
-    VP_CUDA(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
+    VP_CUDA(cudaMalloc(&c->d_work, 12 * sizeof(unsigned long long)));
     VP_CUDA(cudaEventCreate(&c->ev0));
     VP_CUDA(cudaEventCreate(&c->ev1));
     // a 1x1 black environment until init_envmap is called
@@ -442,6 +452,8 @@ int vp_destroy(vp_context* c)
     dev_free(c->env_cdf_y);
     dev_free(c->d_stats);
     dev_free(c->d_work);
+    for (cudaStream_t& r : c->ring)
+        if (r) cudaStreamDestroy(r);
     dev_free(c->host_acc);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -632,15 +644,36 @@ int vp_precompute_opacity(vp_context* c, const float* dir3)
     return VP_OK;
 }
 
+static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
+                     cudaStream_t st, unsigned long long* d_work);
+
 int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
               vp_stream stream)
+{
+    if (!c) return fail(VP_ERR_INVALID, "vp_render: bad arguments");
+    return render_on(c, d_sum, first_frame, n_frames, frame_stride, p, mode, (cudaStream_t)stream, c->d_work + 8 + (c->work_rr++ & 3u));
+}
+
+// the render_kernel shim's launch: see vp_context::ring
+static int render_shim(vp_context* c, void* d_sum, int frame, const vp_param* p, int mode)
+{
+    static const bool overlap = !(getenv("VOLPATH_SHIM_OVERLAP") && atoi(getenv("VOLPATH_SHIM_OVERLAP")) == 0);
+    if (mode != VP_MODE_FAST || !overlap) return vp_render(c, d_sum, frame, 1, 1, p, mode, nullptr);
+    VP_CUDA(cudaSetDevice(c->device));
+    static const unsigned n_ring = getenv("VOLPATH_SHIM_STREAMS") ? (unsigned)std::min(8, std::max(1, atoi(getenv("VOLPATH_SHIM_STREAMS")))) : 4u;
+    const unsigned slot = c->ring_rr++ % n_ring;
+    if (!c->ring[slot]) VP_CUDA(cudaStreamCreate(&c->ring[slot]));
+    return render_on(c, d_sum, frame, 1, 1, p, mode, c->ring[slot], c->d_work + slot);
+}
+
+static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
+                     cudaStream_t st, unsigned long long* d_work)
 {
     if (!c || !d_sum || !p) return fail(VP_ERR_INVALID, "vp_render: bad arguments");
     if (!c->have_volume) return fail(VP_ERR_NO_VOLUME, "vp_render: no volume uploaded");
     if (n_frames <= 0) return VP_OK;
     if (p->width == 0 || p->height == 0 || p->width > 65535 || p->height > 65535) return fail(VP_ERR_INVALID, "vp_render: bad image size");
     VP_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
     VP_CUDA(cudaEventRecord(c->ev0, st));
     if (mode == VP_MODE_PARITY)
     {
@@ -660,10 +693,10 @@ int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int fra
         {
             int nf = (int)(n_frames - f < cap ? n_frames - f : cap);
             if (mode == VP_MODE_WAVE)
-                VP_CUDA(launch_render_wave(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, c->d_work,
+                VP_CUDA(launch_render_wave(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, d_work,
                                            c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
             else
-                VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, c->d_work,
+                VP_CUDA(launch_render_fast(c->S, (float4*)d_sum, first_frame + (int)f * frame_stride, nf, frame_stride, *p, d_work,
                                            c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
             c->launches++;
         }
@@ -956,7 +989,7 @@ void gamma_correct(vp_float4* dst, vp_float4* src, int size, float scale_, float
 void render_kernel(vp_dim3, vp_dim3, vp_float4* d_output, int spp, const vp_param* p)
 {
     SHIM_CTX();
-    SHIM_REPORT(vp_render(c, d_output, spp, 1, 1, p, g_shim_mode, nullptr));
+    SHIM_REPORT(render_shim(c, d_output, spp, p, g_shim_mode));
 }
 
 }  // extern "C"

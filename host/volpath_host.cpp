@@ -50,6 +50,11 @@ extern "C" void free_cuda_buffers();
 #ifdef VOLPATH_B200
 extern "C" void        vp_shim_set_mode(int mode);  // 0 = parity (drop-in identical), 1 = fast
 extern "C" const char* vp_last_error(void);
+// the handle-based core behind the shims (include/volpath.h): frames [first, first + n) of every pixel in ONE launch
+struct vp_context;
+extern "C" vp_context* vp_shim_context(void);
+extern "C" int vp_render(vp_context* ctx, void* d_sum, int first_frame, int n_frames, int frame_stride, const Param* p, int mode,
+                         void* stream);
 #endif
 
 static void die(const char* what)
@@ -128,7 +133,7 @@ int main(int argc, char** argv)
     P.width = 960; P.height = 512; P.density = 800; P.brightness = 1.0f;
     P.albedo = make_float3(1, 1, 1); P.g = 0.877f; P.sigma_t = make_float3(1, 1, 1);
     std::string volume, dump, ppm, envfile;
-    int  blob = 64, spp = 16, envw = 0, envh = 0;
+    int  blob = 64, spp = 16, envw = 0, envh = 0, batch = 1;
     bool quantized = false, linear = true, fast = false;
     for (int i = 1; i < argc; i++)
     {
@@ -145,6 +150,7 @@ int main(int argc, char** argv)
         else if (a == "--g") P.g = (float)atof(next());
         else if (a == "--point") linear = false;
         else if (a == "--fast") fast = true;
+        else if (a == "--batch") batch = atoi(next());  // frames per launch (volpath-b200 build): what a host does for throughput
         else if (a == "--dump") dump = next();
         else if (a == "--ppm") ppm = next();
         else die("unknown option");
@@ -153,7 +159,9 @@ int main(int argc, char** argv)
     vp_shim_set_mode(fast ? 1 : 0);
 #else
     if (fast) die("--fast exists only in the volpath-b200 build");
+    if (batch != 1) die("--batch exists only in the volpath-b200 build");
 #endif
+    if (batch < 1) die("--batch must be >= 1");
 
     // volume -> init_cuda (H.cpp:1332-1344); the caller frees the host copy after the call
     int   nx, ny, nz;
@@ -209,6 +217,17 @@ int main(int argc, char** argv)
             precompute_opacity(sun_dir);
             opacity_dirty = false;
         }
+#ifdef VOLPATH_B200
+        if (batch > 1)
+        {
+            // one launch for frames s .. s + nb - 1; never across the frame-11 boundary, where the opacity table comes in
+            int nb = std::min(batch, spp - s);
+            if (s <= 10) nb = std::min(nb, 11 - s);
+            if (vp_render(vp_shim_context(), d_sum, s, nb, 1, &P, fast ? 1 : 0, nullptr) != 0) die(vp_last_error());
+            s += nb - 1;
+            continue;
+        }
+#endif
         render_kernel(gridSize, blockSize, d_sum, s, P);
     }
     CK(cudaDeviceSynchronize());

@@ -58,3 +58,16 @@ def test_cpp_host_fast_mode_matches_in_the_mean(tmp_path):
     # 256 spp x 6144 pixels: the Monte-Carlo noise of these means is ~1 % (radiance, heavy-tailed) / ~0.3 % (scatters)
     assert abs(fast[..., :3].mean() - ref[..., :3].mean()) <= 0.04 * ref[..., :3].mean()
     assert abs(fast[..., 3].mean() - ref[..., 3].mean()) <= 0.015 * ref[..., 3].mean()
+
+
+def test_cpp_host_batched_launches_render_the_same_samples(tmp_path):
+    """--batch N (vp_render with n_frames = N from the C++ host) renders the same (pixel, frame) samples as one
+    render_kernel call per frame: identical scatter counts, rgb up to the fp32 order of the per-pixel additions."""
+    if not os.path.exists(HOST):
+        pytest.skip("host binary not built (make -C host all)")
+    extra = ["--fast", "--spp", "40", "--density", "600"]
+    one = run(HOST, str(tmp_path / "one.f32"), extra)
+    many = run(HOST, str(tmp_path / "many.f32"), extra + ["--batch", "16"])
+    assert one[..., 3].sum() > 0
+    assert np.array_equal(one[..., 3], many[..., 3])
+    assert np.allclose(one[..., :3], many[..., :3], rtol=1e-5, atol=1e-6)

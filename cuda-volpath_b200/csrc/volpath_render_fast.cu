@@ -29,7 +29,10 @@
 
 namespace vp
 {
-constexpr int      kFastThreads  = 128;
+#ifndef VP_FAST_THREADS
+#define VP_FAST_THREADS 128
+#endif
+constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts below are stated for 128 and scale with it
 // Occupancy: the kernel waits on dependent loads (ncu: 7 of 15 stall cycles per issue are long-scoreboard), so warps
 // per SM matter.  8 / 9 / 10 CTAs of 128 threads: 820 / 878 / 903 M path-samples/s (1/4-dims cloud); with the cold
 // lane state in shared memory (VP_COLD_SMEM) the step block fits 40 registers and 12 CTAs (48 warps) are resident:
@@ -52,7 +55,10 @@ constexpr int      kFastThreads  = 128;
 
 constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
 // chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 10 CTAs (48 registers); the MIS variant 8
-__host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis) { return mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 10 ? 10 : kFastCtasPerSm)); }
+__host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis)
+{
+    return (mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 10 ? 10 : kFastCtasPerSm))) * (128 / kFastThreads);
+}
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim (large launches); small launches claim less, see launch_fast_t
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a

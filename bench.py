@@ -335,6 +335,9 @@ def main():
     achieved = per_launch_bytes / (kernel_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "kernel": "k_render_fast", "kernel_ms": kernel_ms, "bytes_per_path_sample": B, "counts": cnt, "peak_source": peak_src}
+    if args.workload == "c1":
+        roof["note"] = ("C1 is procedural (no density fetches): the kernel is issue-bound, the HBM figure only covers the env texel "
+                        "and the accumulator; SURVEY.md 8d asks for instructions per path there (profiles/README.md)")
     prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(prof):
         t = json.load(open(prof)).get(args.workload)

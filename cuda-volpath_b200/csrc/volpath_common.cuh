@@ -255,6 +255,11 @@ __device__ __forceinline__ void load_octet(const void* pool, size_t cell_index, 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
 
 // slot lookup for cell' = (cx, cy, cz), each in [0, N]
+// LY ("layout") lets a kernel variant fix at compile time what the scene decides at run time: 0 = generic (test the scene),
+// 1 = small volume (flat brick table, float per-cell tables), 2 = large volume (rank directory, half-precision tables);
+// 1 and 2 also imply the linear filter and a sun-clear table.  The tests are warp-uniform branches, but they sit in the
+// fetch and in the segment loop: three instructions each, every time.
+template <int LY = 0>
 __device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, int cz)
 {
     int bx = cx >> kBrickLog2, by = cy >> kBrickLog2, bz = cz >> kBrickLog2;
@@ -262,7 +267,7 @@ __device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, i
     // slot = prefix(word) + popc(bits below).  8 bytes per 32 bricks (C2: 3.2 MB instead of 52 MB) -- the first of
     // the two dependent loads of a density fetch now hits L1/L2 instead of competing with the octets for L2.
     const uint32_t b   = (uint32_t)((bz * S.nby + by) * S.nbx + bx);  // < 2^31 bricks (dims <= 8184)
-    if (S.brick_table) return __ldg(S.brick_table + b);  // small volumes: 4 MB of flat table is cache-resident anyway
+    if (LY == 1 || (LY == 0 && S.brick_table)) return __ldg(S.brick_table + b);  // small volumes: 4 MB of flat table is cache-resident anyway
     const uint2    w   = ldg_keep(S.brick_words + (b >> 5));
     const uint32_t bit = 1u << (b & 31u);
     return (w.x & bit) ? w.y + __popc(w.x & (bit - 1u)) : kEmptyBrick;

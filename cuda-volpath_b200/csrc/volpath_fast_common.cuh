@@ -17,12 +17,12 @@ __device__ __forceinline__ void philox_draw(uint32_t key, uint32_t frame, uint32
 // density at a world position inside the box: one brick-table load + one octet load.  Positions come from
 // o + s * t with t inside the box interval, so cell' = floor(p * N - 0.5) + 1 is within [0, N] up to rounding;
 // a single unsigned range test replaces the six clamps of the texture unit's clamp addressing.
-template <int VT, bool JULIA>
+template <int VT, bool JULIA, int LY = 0>
 __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
 {
     if (JULIA) return julia_density(pos);
     float v[8];
-    if (!S.linear)
+    if (LY == 0 && !S.linear)
     {
         int ix = __float2int_rd(fmaf(pos.x, S.vs_scale.x, S.vs_off.x)) + 1, iy = __float2int_rd(fmaf(pos.y, S.vs_scale.y, S.vs_off.y)) + 1,
             iz = __float2int_rd(fmaf(pos.z, S.vs_scale.z, S.vs_off.z)) + 1;
@@ -37,7 +37,7 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
     int   ix = (int)fx, iy = (int)fy, iz = (int)fz;  // vs_off_lin carries the + 1 of cell' = floor(p * N - 0.5) + 1
     if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
-    uint32_t slot = brick_slot(S, ix, iy, iz);
+    uint32_t slot = brick_slot<LY>(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;
     if (VP_L2_STREAM && VT == kF32 && S.stream_octets)
         ldg256_stream(reinterpret_cast<const float4*>(S.octets) + cell_in_slot(slot, ix, iy, iz) * 2, v);
@@ -56,13 +56,14 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
 
 // opacity table for the production renderers: same 9^3 apron blocks and trilinear weights as fetch_opacity (K.cu:541-542),
 // addressed like density_at (one FMA per axis, FMA lerps)
+template <int LY = 0>
 __device__ __forceinline__ float opacity_at(const Scene& S, float3 pos)
 {
     float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
           zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
     float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
     int   ix = clampi((int)fx, 0, S.nx), iy = clampi((int)fy, 0, S.ny), iz = clampi((int)fz, 0, S.nz);
-    uint32_t slot = brick_slot(S, ix, iy, iz);
+    uint32_t slot = brick_slot<LY>(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;  // only reachable where the density is zero around pos
     const float* q = S.opacity + (size_t)slot * kOpBrickPad + (((iz & (kBrick - 1)) * 9 + (iy & (kBrick - 1))) * 9 + (ix & (kBrick - 1)));
     float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 9), v3 = __ldg(q + 10);
@@ -85,10 +86,11 @@ __device__ __forceinline__ uint32_t bound_cell_index(const Scene& S, float3 pos)
 // local (max, min) at pos from the bound grid of the fast renderer: cells of (1 << cell_log2)^3 voxels, each
 // holding the (max, min) over the cell +-D voxels.  The cell edge is <= D/6, so the window is at most ~7 % wider
 // than the reference's per-voxel window (and identical to it when cell_log2 == 0).
+template <int LY = 0>
 __device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
 {
     const uint32_t i = bound_cell_index(S, pos);
-    if (S.bounds_half)
+    if (LY == 2 || (LY == 0 && S.bounds_half))
     {
         const uint32_t w = ldg_keep(S.bounds_half + i);
         return __half22float2(*reinterpret_cast<const __half2*>(&w));
@@ -96,10 +98,11 @@ __device__ __forceinline__ float2 bounds_at(const Scene& S, float3 pos)
     return ldg_keep(S.bounds_cell + i);
 }
 // distance from pos toward the sun after which only vacuum follows (plus the point-to-cell-centre margin)
+template <int LY = 0>
 __device__ __forceinline__ float sun_clear_at(const Scene& S, float3 pos)
 {
     const uint32_t i = bound_cell_index(S, pos);
-    if (S.sun_clear_half) return __half2float(__ushort_as_half(ldg_keep(S.sun_clear_half + i))) + S.clear_margin;
+    if (LY == 2 || (LY == 0 && S.sun_clear_half)) return __half2float(__ushort_as_half(ldg_keep(S.sun_clear_half + i))) + S.clear_margin;
     return ldg_keep(S.sun_clear + i) + S.clear_margin;
 }
 

@@ -122,7 +122,7 @@ struct ColdF
     __device__ __forceinline__ void operator=(float v) const { *p = v; }
 };
 
-template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS>
+template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS, int LY>
 __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 {
                     if (STATS) c_seg++;
                     float  seg_end = JULIA ? t_ex : fminf(dist + kSearchRadius, t_ex);
-                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at(S, o + s * dist);
+                    float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at<LY>(S, o + s * dist);
                     if (bnd.x <= 0.0f)
                     {
                         // no medium within reach: the walk passes with probability 1; -bnd.x is how far it may go
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 float      den  = 0.0f;
                 if (!past)
                 {
-                    den = density_at<VT, JULIA>(S, pos) * dens;
+                    den = density_at<VT, JULIA, LY>(S, pos) * dens;
                     if (STATS)
                     {
                         if (st & kShadow) c_shadow++; else c_track++;
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 if ((int)rng.frame > 10 && n > 20)  // K.cu:2183: precomputed sun opacity
                 {
                     if (STATS) c_op++;
-                    float  tau = (!JULIA && S.have_opacity) ? opacity_at(S, o) : 0.0f;
+                    float  tau = (!JULIA && S.have_opacity) ? opacity_at<LY>(S, o) : 0.0f;
                     float3 a   = GRAY ? f3(__expf(-sig_t.x * dens * tau))
                                       : f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
                     L          = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     dist = 0.0f;
                     lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
                     // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
-                    if (!JULIA && S.sun_clear) lim = fminf(lim, sun_clear_at(S, o));
+                    if (!JULIA && (LY != 0 || S.sun_clear)) lim = fminf(lim, sun_clear_at<LY>(S, o));
                     st   = kModeStep | kShadow;
                 }
             }
@@ -581,10 +581,21 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
     unsigned long long ctas  = (want + kFastThreads / 32 - 1) / (kFastThreads / 32);
     unsigned int       grid  = (unsigned int)(ctas < (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS) ? ctas : (unsigned long long)num_sms * fast_ctas_per_sm(GRAY, MIS));
     if (grid < 1) grid = 1;
+    // layout known at compile time for the two production cases (see brick_slot); everything else tests the scene
+    int ly = 0;
+    if (!JULIA && !MIS && !d_stats && S.linear && S.sun_clear)
+    {
+        if (S.brick_table && !S.bounds_half && !S.sun_clear_half) ly = 1;
+        if (!S.brick_table && S.bounds_half && S.sun_clear_half) ly = 2;
+    }
     if (d_stats)
-        k_render_fast<VT, JULIA, GRAY, MIS, true><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, claim);
+        k_render_fast<VT, JULIA, GRAY, MIS, true, 0><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, claim);
+    else if (!JULIA && !MIS && ly == 1)
+        k_render_fast<VT, false, GRAY, false, false, 1><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
+    else if (!JULIA && !MIS && ly == 2)
+        k_render_fast<VT, false, GRAY, false, false, 2><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
     else
-        k_render_fast<VT, JULIA, GRAY, MIS, false><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
+        k_render_fast<VT, JULIA, GRAY, MIS, false, 0><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
     return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@
 // for the longest path of every warp and of every launch.  Here:
 //
 //   * PERSISTENT WARPS, GLOBAL WORK POOL.  The grid is sized to the SMs; a path-sample is an item
-//     (pixel, frame) of one global index space; each warp claims ranges of 256 items with ONE atomic and hands
+//     (pixel, frame) of one global index space; each warp claims ranges of 32..256 items (by launch size) with ONE atomic and hands
 //     them to lanes as they finish (ballot/popc ranking).  No lane idles before the pool is empty; nothing
 //     waits for a launch boundary (all frames of a call are one launch).
 //   * WARP-LEVEL EVENT BINNING.  A lane is in one of four states -- new path, segment setup, walk step,
@@ -24,6 +24,10 @@
 //   * counter-based Philox2x32-10: key = pixel, counter = (draw index, frame); no carried RNG state.
 //   * density comes from the octet store: one table load + one 32/16/8-byte load per trilinear sample.
 //   * one vector atomic (red.global.add.v4.f32) per finished path into the float4 sum.
+//   * rare work runs where it is batched best, not where it arises: the environment lookup of an escaped path waits
+//     for the path block, the sun contribution of a finished shadow walk for the head of the segment block.
+//   * the storage layout (flat brick table / rank directory, float / half per-cell tables) is a template parameter
+//     of the production variants (LY), so the fetch and the segment loop carry no layout tests.
 #include "volpath_fast_common.cuh"
 #include "volpath_kernels.h"
 

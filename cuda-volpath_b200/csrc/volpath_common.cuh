@@ -230,7 +230,17 @@ template <> struct OctetBytes<kF32> { static constexpr int value = 32; };
 template <int VT>
 __device__ __forceinline__ void load_octet(const void* pool, size_t cell_index, float v[8])
 {
-    if (VT == kF32)
+#ifndef VP_OCTET_256
+#define VP_OCTET_256 0  // one 256-bit load per fp32 octet (Blackwell) instead of two 128-bit ones: measured, see profiles/README.md
+#endif
+    if (VT == kF32 && VP_OCTET_256)
+    {
+        const float4* p = reinterpret_cast<const float4*>(pool) + cell_index * 2;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    }
+    else if (VT == kF32)
     {
         const float4* p = reinterpret_cast<const float4*>(pool) + cell_index * 2;
         float4        a = __ldg(p), b = __ldg(p + 1);

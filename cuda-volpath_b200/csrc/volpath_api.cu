@@ -240,7 +240,13 @@ static int update_sun_clear(vp_context* c)
     S.sun_clear_half = nullptr;
     if (c->bounds_half)
     {
-        if (!c->sun_clear_half) VP_CUDA(cudaMalloc(&c->sun_clear_half, cells * sizeof(uint16_t)));
+        if (!c->sun_clear_half && cudaMalloc(&c->sun_clear_half, cells * sizeof(uint16_t)) != cudaSuccess)
+        {
+            cudaGetLastError();  // no room for the copy: both tables stay float (the renderers take the pair together)
+            dev_free(c->bounds_half);
+            S.bounds_half = nullptr;
+            return VP_OK;
+        }
         VP_CUDA(launch_pack_clear_half(c->sun_clear, c->sun_clear_half, cells, 0));
         c->launches++;
         VP_CUDA(cudaDeviceSynchronize());
@@ -379,14 +385,18 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         if (c->bounds_cell && want)
         {
             const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
-            int *d_over = nullptr, h_over = 0;
-            VP_CUDA(cudaMalloc(&d_over, sizeof(int)));
-            VP_CUDA(cudaMemset(d_over, 0, sizeof(int)));
-            VP_CUDA(cudaMalloc(&c->bounds_half, cells * sizeof(uint32_t)));
-            VP_CUDA(launch_pack_bounds_half(c->bounds_cell, c->bounds_half, cells, d_over, 0));
-            VP_CUDA(cudaMemcpy(&h_over, d_over, sizeof(int), cudaMemcpyDeviceToHost));
-            cudaFree(d_over);
-            if (h_over) dev_free(c->bounds_half);  // values beyond the half range: stay with the float tables
+            // the copies are an optimisation: out of memory or values beyond the half range -> stay with the float tables
+            int *d_over = nullptr, h_over = 1;
+            if (cudaMalloc(&d_over, sizeof(int)) == cudaSuccess && cudaMalloc(&c->bounds_half, cells * sizeof(uint32_t)) == cudaSuccess &&
+                cudaMemset(d_over, 0, sizeof(int)) == cudaSuccess &&
+                launch_pack_bounds_half(c->bounds_cell, c->bounds_half, cells, d_over, 0) == cudaSuccess)
+            {
+                c->launches++;
+                if (cudaMemcpy(&h_over, d_over, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) h_over = 1;
+            }
+            cudaGetLastError();
+            if (d_over) cudaFree(d_over);
+            if (h_over) dev_free(c->bounds_half);
             S.bounds_half = c->bounds_half;
         }
     }

@@ -1,20 +1,29 @@
 #!/usr/bin/env python3
 """bench.py -- path-samples/s of the render hot path (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c2q|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3a|c3b|c4|c5|c2q|c2e]
 
 A "step" is one pass of the hot path over one batch: --frames-per-step frames (sample indices) of the whole image.
-Default workload (N = 1) is config C2 of BASELINE.json: synthetic fBm cloud at WDAS dims 1987x1351x2449 fp32,
-1920x1080, default sun/sky, camera and Param of the reference.  With N > 1 every rank holds the whole
-volume and renders its own strided subset of the frames (sample-index sharding); the float4 sums are combined by one
-NCCL reduce per step inside the timed region.
 
-`value`   : device-timed (CUDA events on the launch stream), accumulator resident in HBM.
-`e2e`     : the same step through the host-buffer C-ABI call vp_render_to_host (pinned host float4 sum in and out).
+N = 1 (default workload c2 = config C2 of BASELINE.json: synthetic fBm cloud at WDAS dims 1987x1351x2449 fp32,
+1920x1080, default sun/sky, camera and Param of the reference): one step = one launch of k_render_fast.
+
+N > 1 (default workload c5 = config C5: the same volume at 3840x2160, STRONG scaling): the frames of a step are split
+over the ranks by sample index (rank r renders frames r, r + N, ...; volume replicated), so the total work per step does
+not depend on N.  Every rank renders into one of two accumulators; the library's own NCCL reduce (vp_reduce_nccl, C ABI)
+runs on a side stream and overlaps the next step's render; the root adds the reduced step into the image.  All K reduces
+are inside the timed region (the final event waits for the last one).
+
+`value`   : device-timed (CUDA events on the launch stream), accumulators resident in HBM, max over ranks.
+`e2e`     : the same steps through the host-buffer C-ABI call vp_render_to_host (pinned host float4 sum in and out).
 `roofline`: algorithmic bytes per path-sample (SURVEY.md 8d formula, L/S/O/E counted by the instrumented reference
             kernel, profiles/ref_counters.json) x path-samples/s vs the measured HBM copy peak.
+`check`   : the benchmarked kernel variant (rank directory + half tables + coarse bound cells on the full grid) against
+            the reference-faithful renderer (VP_MODE_PARITY, per-voxel windows) at FULL dims on a 480x270 subset.
 `cpu_baseline` / `--impl reference`: the reference's own kernel source compiled for the host (oracle/_ref, OpenMP over
-            all cores) on a bounded sample of the same cloud family.
+            all cores) on a bounded sample of the same cloud family; `gpu_same_sample` = this repo's GPU arm on exactly
+            that sample, so one ratio in the line is like for like.
+`ref_cuda`: the reference's CUDA kernel rebuilt for sm_100 beside ours on the same GPU and scene, incl. time-to-RMSE.
 """
 import argparse
 import ctypes
@@ -31,14 +40,21 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 C2_DIMS = (1987, 1351, 2449)
 WORKLOADS = {
-    # name: (dims, image, description)
-    "c2": (C2_DIMS, (1920, 1080), "C2: synthetic fBm cloud 1987x1351x2449 fp32, 1920x1080, default sun/sky"),
-    "c2q": ((497, 338, 612), (1920, 1080), "C2 cloud family at 1/4 dims 497x338x612 fp32, 1920x1080"),
-    "c2e": ((248, 168, 306), (480, 270), "C2 cloud family at 1/8 dims 248x168x306 fp32, 480x270"),
-    "c5": (C2_DIMS, (3840, 2160), "C5: synthetic fBm cloud 1987x1351x2449 fp32, 3840x2160, sample-split"),
-    "c1": (None, (512, 512), "C1: procedural Julia set (no-OpenVDB build), 512x512"),
+    # name: (dims, image, material preset / overrides, description)
+    "c2": (C2_DIMS, (1920, 1080), {}, "C2: synthetic fBm cloud 1987x1351x2449 fp32, 1920x1080, default sun/sky"),
+    "c3a": (C2_DIMS, (1920, 1080), {"material": 8},
+            "C3: chromatic medium Mat(0.74,0.88,1.01 / 0.032,0.17,0.48) on the C2 cloud, 1920x1080"),
+    "c3b": (C2_DIMS, (1920, 1080), {"material": 4},
+            "C3: strongly chromatic medium Mat(0.18,0.07,0.03 / 0.061,0.97,1.45) on the C2 cloud, 1920x1080"),
+    "c4": (C2_DIMS, (1920, 1080), {"albedo": 0.999, "density": 3000.0},
+           "C4: albedo 0.999, density 3000 (deep paths, opacity-table branch) on the C2 cloud, 1920x1080"),
+    "c5": (C2_DIMS, (3840, 2160), {}, "C5: synthetic fBm cloud 1987x1351x2449 fp32, 3840x2160, sample-split"),
+    "c2q": ((497, 338, 612), (1920, 1080), {}, "C2 cloud family at 1/4 dims 497x338x612 fp32, 1920x1080"),
+    "c2e": ((248, 168, 306), (480, 270), {}, "C2 cloud family at 1/8 dims 248x168x306 fp32, 480x270"),
+    "c1": (None, (512, 512), {}, "C1: procedural Julia set (no-OpenVDB build), 512x512"),
 }
 CLOUD_SEED = 0
+CPU_SAMPLE_DIMS, CPU_SAMPLE_IMAGE = (248, 168, 306), (480, 270)
 
 
 def peaks():
@@ -56,7 +72,7 @@ def algorithmic_bytes_per_path(workload, frames_per_rmw):
     L, S, O, E = 118.0, 60.0, 5.6, 1.0
     if os.path.exists(p):
         j = json.load(open(p))
-        key = "c1" if workload == "c1" else "cloud"
+        key = workload if workload in j else ("c1" if workload == "c1" else "cloud")
         if key in j:
             c = j[key]
             L, S, O, E = c["L"], c["S"], c["O"], c["E"]
@@ -101,7 +117,26 @@ def scene_inputs(vp):
     return env, sun_dir, sun_power, vp.inv_view_matrix()
 
 
-def host_reference_run(args, workload_desc):
+def workload_param(vp, W, H, over):
+    P = vp.default_param(W, H)
+    if "material" in over:
+        P = vp.mat(P, *vp.MATERIALS[over["material"]])
+    if "albedo" in over:
+        P.albedo[:] = [over["albedo"]] * 3
+    if "density" in over:
+        P.density = over["density"]
+    return P
+
+
+def cpu_sample_desc(julia, fps):
+    if julia:
+        return "C1 Julia set (no-OpenVDB build), 256x256, frames 0..%d per step, host cores" % (fps - 1)
+    return ("C2 cloud family at 1/8 dims (%dx%dx%d fp32, the dims of the reference's own wdas_cloud_eighth asset), %dx%d, "
+            "frames 0..%d per step (<= 10: shadow walks, no opacity table), host cores"
+            % (CPU_SAMPLE_DIMS + CPU_SAMPLE_IMAGE + (fps - 1,)))
+
+
+def host_reference_run(args):
     """The reference's own kernel source compiled by g++ (oracle/_ref/libvolpath_ref_host*.so), OpenMP over all host
     cores, on a bounded sample: the C2 cloud family at 1/8 dims (248x168x306 fp32, the dims the reference's own asset
     wdas_cloud_eighth has), 480x270 -- the full 26 GB volume and its 52 GB CPU bound volume do not fit a host run."""
@@ -130,25 +165,23 @@ def _host_reference_run(args, julia, name):
         ref, kind = RefHost(julia=julia), "reference"
     else:
         ref, kind = Oracle(), "port"
+    over = WORKLOADS[args.workload][2]
     if julia:
         W, H = 256, 256
         ref.set_julia()
-        sample = "Julia set, 256x256, %d frame(s) per step"
     else:
-        W, H = 480, 270
-        vol = Oracle().fbm_cloud(248, 168, 306, seed=CLOUD_SEED)
+        W, H = CPU_SAMPLE_IMAGE
+        vol = Oracle().fbm_cloud(*CPU_SAMPLE_DIMS, seed=CLOUD_SEED)
         ref.set_volume(vol, False, None, linear=True)
-        sample = "C2 cloud family at 1/8 dims (248x168x306 fp32), 480x270, frames 0..%d-1 per step (shadow walks, no opacity table)"
     ref.set_envmap(env)
     ref.set_sun(sun_dir, sun_power)
     ref.set_inv_view(view)
-    P = vp.default_param(W, H)
+    P = workload_param(vp, W, H, over)
     cores = int(os.environ.get("OMP_NUM_THREADS", "0") or 0) or (os.cpu_count() or 1)
-    fps = max(1, args.ref_frames)
     acc = np.zeros((H, W, 4), np.float32)
     # frames 0..10 only: from frame 11 on the kernel reads the precomputed sun-opacity table (K.cu:2183), whose
     # construction (_precompute_opacity: ~10^10 emulated texture fetches at these dims) is not feasible on host cores
-    fps = min(fps, 11)
+    fps = min(max(1, args.ref_frames), 11)
     for _ in range(args.warmup):
         ref.render(P, 0, 1, accum=acc)
     t0 = time.perf_counter()
@@ -169,8 +202,86 @@ def _host_reference_run(args, julia, name):
         omp.omp_set_num_threads(cores)
     except Exception:
         pass
-    return value, dt, dict(value=value, unit="path-samples/s", cores=cores, kind=kind, sample=sample % fps,
-                           single_thread_value=single)
+    sample = cpu_sample_desc(julia, fps)
+    return value, dt, sample, dict(value=value, unit="path-samples/s", cores=cores, kind=kind, sample=sample,
+                                   single_thread_value=single, frames_per_step=fps,
+                                   mean_scatters_per_path=float(acc[..., 3].sum() / (W * H * (fps * args.steps + args.warmup + (1 if single else 0)))))
+
+
+def gpu_same_sample(vp, device, workload, fps, over):
+    """This repo's GPU arm on EXACTLY the cpu_baseline sample (same volume, image, frames 0..fps-1, host buffers in and
+    out through vp_render_to_host): the like-for-like ratio against the host build of the reference."""
+    import numpy as np
+
+    r = vp.Renderer(device)
+    env, sun_dir, sun_power, view = scene_inputs(vp)
+    if workload == "c1":
+        W, H = 256, 256
+        r.set_julia()
+    else:
+        W, H = CPU_SAMPLE_IMAGE
+        r.generate_cloud(*CPU_SAMPLE_DIMS, seed=CLOUD_SEED, bounds=vp.BOUNDS_CELL)
+    r.set_texture_filter_mode(True)
+    r.init_envmap(env)
+    r.set_sun(sun_dir, sun_power)
+    r.copy_inv_view_matrix(view)
+    P = workload_param(vp, W, H, over)
+    acc = np.zeros((H, W, 4), np.float32)
+    r.render(P, 0, fps, accum=acc)  # warm-up
+    acc[:] = 0
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r.render(P, 0, fps, accum=acc)
+    dt = time.perf_counter() - t0
+    out = {"value": W * H * fps * reps / dt, "unit": "path-samples/s", "ms_per_call": 1e3 * dt / reps,
+           "mean_scatters_per_path": float(acc[..., 3].sum() / (W * H * fps * reps)),
+           "note": "vp_render_to_host, host float4 sum in and out; a %d-sample call is launch- and tail-bound on a B200" % (W * H * fps)}
+    r.close()
+    return out
+
+
+def check_block(vp, device, dims, over, subset=(480, 270), frames=256):
+    """the variant the bench times (k_render_fast on the FULL grid: rank directory, half-precision
+    per-cell tables, bound cells of 8^3 voxels, swept fp16 opacity octets) against the reference-faithful renderer
+    (k_render_parity: reference RNG, draw order and segmenting, the reference's own per-voxel +-50-voxel windows
+    K.cu:1626-1661, the bit-faithful opacity table) on the same full-dims volume: 480x270, frames 12..12+frames-1."""
+    import numpy as np
+
+    r = vp.Renderer(device)
+    t0 = time.perf_counter()
+    env, sun_dir, sun_power, view = scene_inputs(vp)
+    r.generate_cloud(*dims, seed=CLOUD_SEED, bounds=vp.BOUNDS_CELL | vp.BOUNDS_VOXEL)
+    r.set_texture_filter_mode(True)
+    r.init_envmap(env)
+    r.set_sun(sun_dir, sun_power)
+    r.copy_inv_view_matrix(view)
+    r.precompute_opacity(sun_dir)
+    r.sync()
+    setup = time.perf_counter() - t0
+    st = r.volume_stats()
+    W, H = subset
+    P = workload_param(vp, W, H, over)
+    fast = r.render(P, 12, 4 * frames, mode=vp.MODE_FAST)      # 4x the samples: the fast estimate's noise is not the limit
+    par_a = r.render(P, 12, frames // 2, mode=vp.MODE_PARITY)
+    par_b = r.render(P, 12 + frames // 2, frames - frames // 2, mode=vp.MODE_PARITY)
+    r.close()
+    par = par_a + par_b
+    n_f, n_p = W * H * 4 * frames, W * H * frames
+    sf, sp = fast[..., 3].sum() / n_f, par[..., 3].sum() / n_p
+    mf, mp = fast[..., :3].sum() / n_f, par[..., :3].sum() / n_p
+    half = W * H * (frames // 2)
+    noise_s = abs(par_a[..., 3].sum() / half - par_b[..., 3].sum() / (n_p - half)) / sp
+    noise_m = abs(par_a[..., :3].sum() / half - par_b[..., :3].sum() / (n_p - half)) / mp
+    return {"what": "k_render_fast (benchmarked layout: rank directory, half tables, %d^3-voxel bound cells, fp16 opacity octets) vs "
+                    "k_render_parity (per-voxel windows) on the full %dx%dx%d grid, %dx%d, frames 12..%d (fast: 4x as many)"
+                    % ((st["bound_cell_voxels"],) + tuple(dims) + (W, H, 12 + frames - 1)),
+            "mean_scatters_fast": float(sf), "mean_scatters_parity": float(sp), "scatter_rel": float(abs(sf - sp) / sp),
+            "image_mean_fast": float(mf), "image_mean_parity": float(mp), "mean_rel": float(abs(mf - mp) / mp),
+            "parity_half_vs_half": {"scatter_rel": float(noise_s), "mean_rel": float(noise_m)},
+            "tolerance": {"scatter_rel": 0.01, "mean_rel": 0.005},
+            "ok": bool(abs(sf - sp) / sp <= 0.01 and abs(mf - mp) / mp <= 0.005 + noise_m),
+            "bounds_voxel_bytes": st["bounds_voxel_bytes"], "setup_s": round(setup, 2)}
 
 
 def main():
@@ -181,30 +292,35 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=256,
-                    help="frames (sample indices) of the whole image per step = per launch; the default 4 steps x 256 are the 1024 spp of config C2")
+                    help="frames (sample indices) of the whole image per step; N = 1: one launch; N > 1: split over the ranks")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1: strong (default) = a step is --frames-per-step frames in total; weak = per GPU")
     ap.add_argument("--store", default="f32", choices=["f32", "f16"])
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the host reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--truth-spp", type=int, default=4096, help="spp of the reference-kernel ground truth of the time-to-RMSE leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
-        args.workload = "c2"
-    dims, (W, H), desc = WORKLOADS[args.workload]
+        args.workload = "c2" if max(world, args.gpus) == 1 else "c5"
+    dims, (W, H), over, desc = WORKLOADS[args.workload]
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         # torchrun pins OMP_NUM_THREADS=1; the reference arm uses every host core it can
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-        value, dt, cb = host_reference_run(args, desc)
+        value, dt, sample, cb = host_reference_run(args)
         line = {"impl": "reference", "metric": "path-samples/s", "value": value, "unit": "path-samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc}, "cpu_baseline": cb,
+                "config": {"workload": "bounded CPU sample of %s: %s" % (args.workload.upper(), sample), "b200_arm_workload": desc},
+                "cpu_baseline": cb,
                 "e2e": {"value": value, "unit": "path-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -219,7 +335,7 @@ def main():
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
@@ -228,8 +344,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    t_job = time.perf_counter()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    strong = world > 1 and (args.scaling or "strong") == "strong"
     r = vp.Renderer(local)
     env, sun_dir, sun_power, view = scene_inputs(vp)
     t_setup = time.perf_counter()
@@ -245,21 +363,52 @@ def main():
     r.precompute_opacity(sun_dir)
     r.sync()
     t_setup = time.perf_counter() - t_setup
+    opacity_ms = r.opacity_build_ms()
     stats = r.volume_stats() if dims is not None else {}
-    P = vp.default_param(W, H)
+    P = workload_param(vp, W, H, over)
     fps = args.frames_per_step
-    acc = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)
-    stream = torch.cuda.current_stream().cuda_stream
+    step_frames = fps if (world == 1 or strong) else fps * world  # frames of one step, all ranks together
+    main_stream = torch.cuda.current_stream()
+    stream = main_stream.cuda_stream
+    total = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)  # the image (root; N = 1: the accumulator itself)
+    if world > 1:
+        # the library's own NCCL communicator (C ABI); torch.distributed only carries the unique id and the barriers
+        vp.init_nccl_from_torch(r)
+        bufs = [torch.zeros(H, W, 4, device="cuda", dtype=torch.float32) for _ in range(2)]
+        side = torch.cuda.Stream()
+        ev_render = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        used = [False, False]
 
     def step(k):
-        # global frames of step k: [k*fps*world, (k+1)*fps*world); this rank takes every world-th one
-        first, count, stride = vp.frames_for_rank(k * fps * world, fps * world, rank, world)
-        r.render_kernel(acc.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
+        # global frames of step k: [k * step_frames, (k + 1) * step_frames); this rank takes every world-th one
+        first, count, stride = vp.frames_for_rank(k * step_frames, step_frames, rank, world)
+        if world == 1:
+            r.render_kernel(total.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
+            return
+        b = k & 1
+        if used[b]:
+            main_stream.wait_event(ev_free[b])  # its reduce (step k - 2) has drained and zeroed the buffer
+        r.render_kernel(bufs[b].data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
+        ev_render[b].record(main_stream)
+        side.wait_event(ev_render[b])
+        r.reduce_nccl(bufs[b].data_ptr(), bufs[b].data_ptr() if rank == 0 else None, W * H, root=0, stream=side.cuda_stream)
+        if rank == 0:
+            vp.lib.check(r.L.vp_accumulate(r.h, total.data_ptr(), bufs[b].data_ptr(), W * H, side.cuda_stream))
+        with torch.cuda.stream(side):
+            bufs[b].zero_()
+        ev_free[b].record(side)
+        used[b] = True
+
+    def drain():
         if world > 1:
-            vp.reduce_accumulators(acc, dst=0)
+            for b in range(2):
+                if used[b]:
+                    main_stream.wait_event(ev_free[b])
 
     for k in range(args.warmup):
         step(k)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -268,13 +417,14 @@ def main():
     sampler.start()
     n0 = r.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
+    t_wall = time.perf_counter()
     e0.record()
     for k in range(args.warmup, args.warmup + args.steps):
         step(k)
-        kern_ms.append(None)
+    drain()
     e1.record()
     torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -283,87 +433,125 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([ms, t_setup], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    paths = W * H * fps * world * args.steps
+        ms, t_setup_max = float(t[0].item()), float(t[1].item())
+    else:
+        t_setup_max = t_setup
+    paths = W * H * step_frames * args.steps
     value = paths / (ms * 1e-3)
+    # what the image holds: scatter counts are integers, so the mean scatter count per path is exact evidence that every
+    # (pixel, frame) item was rendered once (N > 1: on the root, after the reduces)
+    img_stats = None
+    if rank == 0:
+        n_img = W * H * step_frames * (args.warmup + args.steps)
+        img_stats = {"mean_scatters_per_path": float(total[..., 3].double().sum().item() / n_img),
+                     "image_mean": float(total[..., :3].double().sum().item() / (3 * n_img)), "frames_in_image": step_frames * (args.warmup + args.steps)}
 
-    # kernel-only average launch duration for the roofline (the step IS one launch of k_render_fast)
+    # kernel-only average launch duration for the roofline: this rank's render launch alone
     kms = []
-    for k in range(args.warmup + args.steps, args.warmup + args.steps + 2):
-        first, count, stride = vp.frames_for_rank(k * fps * world, fps * world, rank, world)
-        r.render_kernel(acc.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
+    first, count, stride = vp.frames_for_rank(10 ** 6, step_frames, rank, world)
+    scratch = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)
+    for k in range(2):
+        r.render_kernel(scratch.data_ptr(), first + k * step_frames, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
         kms.append(r.last_kernel_ms())
     kernel_ms = sum(kms) / len(kms)
+    kernel_paths = W * H * count
     if world == 1:
         kernel_ms = ms / args.steps  # the timed region is exactly `steps` launches of k_render_fast: CUDA events over it
+    del scratch
 
     # e2e: host-buffer call, pinned float4 sum in and out
-    e2e = None
-    if rank == 0 or world > 1:
-        h_sum = torch.zeros(H, W, 4, dtype=torch.float32).pin_memory()
-        e2e_steps = max(2, min(args.steps, 4))
-        # one untimed call: first-use costs of the host-buffer path (device accumulator allocation, copy engines)
-        first, count, stride = vp.frames_for_rank(999 * fps * world, fps * world, rank, world)
+    h_sum = torch.zeros(H, W, 4, dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 4))
+    # one untimed call: first-use costs of the host-buffer path (device accumulator allocation, copy engines)
+    first, count, stride = vp.frames_for_rank(999 * step_frames, step_frames, rank, world)
+    vp.lib.check(r.L.vp_render_to_host(r.h, h_sum.data_ptr(), first, count, stride, ctypes.byref(P), vp.MODE_FAST))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        first, count, stride = vp.frames_for_rank((1000 + k) * step_frames, step_frames, rank, world)
+        r.copy_inv_view_matrix(view)
         vp.lib.check(r.L.vp_render_to_host(r.h, h_sum.data_ptr(), first, count, stride, ctypes.byref(P), vp.MODE_FAST))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            first, count, stride = vp.frames_for_rank((1000 + k) * fps * world, fps * world, rank, world)
-            r.copy_inv_view_matrix(view)
-            vp.lib.check(r.L.vp_render_to_host(r.h, h_sum.data_ptr(), first, count, stride, ctypes.byref(P), vp.MODE_FAST))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": W * H * fps * world * e2e_steps / dt, "unit": "path-samples/s",
-               "h2d_bytes_per_step": W * H * 16 + 44 + 48, "d2h_bytes_per_step": W * H * 16}
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": W * H * step_frames * e2e_steps / dt, "unit": "path-samples/s",
+           "h2d_bytes_per_step": W * H * 16 + 44 + 48, "d2h_bytes_per_step": W * H * 16}
+    if world > 1:
+        e2e["note"] = "per rank: its own pinned host float4 sum in and out around its share of the step (bytes are per rank)"
 
     if rank != 0:
+        r.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = peaks()
-    B, cnt = algorithmic_bytes_per_path(args.workload, fps)
-    per_launch_bytes = B * W * H * fps
+    B, cnt = algorithmic_bytes_per_path(args.workload, max(count, 1))
+    per_launch_bytes = B * kernel_paths
     achieved = per_launch_bytes / (kernel_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "k_render_fast", "kernel_ms": kernel_ms, "bytes_per_path_sample": B, "counts": cnt, "peak_source": peak_src}
+            "kernel": "k_render_fast", "kernel_ms": kernel_ms, "bytes_per_path_sample": B, "counts": cnt, "peak_source": peak_src,
+            "path_samples_per_launch": kernel_paths}
     if args.workload == "c1":
         roof["note"] = ("C1 is procedural (no density fetches): the kernel is issue-bound, the HBM figure only covers the env texel "
                         "and the accumulator; SURVEY.md 8d asks for instructions per path there (profiles/README.md)")
     prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(prof):
         t = json.load(open(prof)).get(args.workload)
-        if t and fps == t.get("frames", 64) and (W, H) == (1920, 1080):
+        if t and count == t.get("frames", 64) and (W, H) == (1920, 1080):
             roof["traffic"] = t["dram_bytes_per_launch"]  # bytes per launch, same launch shape as `achieved`
             roof["traffic_source"] = t["source"]
-        roof["algorithmic_bytes_per_launch"] = per_launch_bytes
+    roof["algorithmic_bytes_per_launch"] = per_launch_bytes
 
+    par = ("one GPU" if world == 1 else
+           "sample-index sharding x%d (%s scaling: %d frames per step %s), vp_reduce_nccl per step on a side stream, "
+           "double-buffered accumulators" % (world, "strong" if strong else "weak", step_frames, "in total" if strong else "= %d per GPU" % fps))
     line = {"metric": "path-samples/s", "value": value, "unit": "path-samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if (strong or world == 1) else "weak",
             "vs_baseline": None, "dtype": "f32" if args.store == "f32" else "f16", "data": "synthetic",
-            "config": {"workload": desc, "frames_per_step_per_gpu": fps, "mode": "fast (megakernel)", "store": args.store,
+            "config": {"workload": desc, "frames_per_step": step_frames, "frames_per_step_per_gpu": step_frames // world if world > 1 else fps,
+                       "mode": "fast (megakernel)", "store": args.store,
                        "l2": "inputs larger than L2 (octet store %.1f GB)" % (stats.get("octet_bytes", 0) / 1e9),
-                       "parallelism": "sample-index sharding x%d, NCCL reduce per step" % world,
-                       "volume": stats, "setup_s": round(t_setup, 2)},
-            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
+                       "parallelism": par, "volume": stats, "setup_s": round(t_setup_max, 2), "opacity_build_s": round(opacity_ms * 1e-3, 3),
+                       "wall_to_image_s": round(t_setup_max + ms * 1e-3, 2),
+                       "wall_note": "setup (cloud, bricks, bounds, sun tables: per GPU, replicated) + the timed region"},
+            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "image": img_stats}
+    if world == 1:
+        line["scaling"] = "weak"  # one GPU: per-GPU work is what it is
 
     r.close()
-    del acc
+    del total
     torch.cuda.empty_cache()
+    if world == 1 and not args.no_check and dims is not None and dims == C2_DIMS:
+        try:
+            line["check"] = check_block(vp, local, dims, over)
+        except Exception as e:  # out of memory on a smaller GPU, ...
+            line["check"] = {"unavailable": repr(e)[:300]}
+        torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
         j = run_tool([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
                       "--steps", "2", "--warmup", "1"], 240)
-        line["cpu_baseline"] = j.get("cpu_baseline", j)
+        cb = j.get("cpu_baseline", j)
+        if "value" in cb:
+            try:
+                g = gpu_same_sample(vp, local, args.workload, cb.get("frames_per_step", 8), over)
+                g["ratio_vs_cpu_baseline"] = g["value"] / cb["value"]
+                cb["gpu_same_sample"] = g
+            except Exception as e:
+                cb["gpu_same_sample"] = {"unavailable": repr(e)[:300]}
+        line["cpu_baseline"] = cb
     if world == 1 and not args.no_ref_cuda and dims is not None:
-        line["ref_cuda"] = ref_cuda_compare(local, fps)
+        line["ref_cuda"] = ref_cuda_compare(local, fps, over, args.truth_spp)
+        if isinstance(line["ref_cuda"], dict) and "rmse" in line["ref_cuda"]:
+            line["rmse"] = line["ref_cuda"]["rmse"]
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -383,13 +571,21 @@ def run_tool(cmd, timeout):
         return {"unavailable": repr(e)[:300]}
 
 
-def ref_cuda_compare(device, fps):
+def ref_cuda_compare(device, fps, over, truth_spp):
     """The reference's own CUDA kernel rebuilt for sm_100, beside ours on the same scene and GPU
-    (tools/compare_ref_cuda.py, C2 cloud family at 1/4 dims -- what the reference's layout can hold)."""
+    (tools/compare_ref_cuda.py, C2 cloud family at 1/4 dims -- what the reference's layout can hold), and the
+    time-to-RMSE leg against a high-spp image of the reference kernel."""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libvolpath_ref_cuda.so")):
         return {"unavailable": "oracle/_ref/libvolpath_ref_cuda.so not built"}
-    return run_tool([sys.executable, os.path.join(ROOT, "tools", "compare_ref_cuda.py"), "--frames", str(fps),
-                     "--device", str(device)], 240)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "compare_ref_cuda.py"), "--frames", str(fps), "--device", str(device),
+           "--rmse-truth-spp", str(truth_spp)]
+    if "material" in over:
+        cmd += ["--material", str(over["material"])]
+    if "albedo" in over:
+        cmd += ["--albedo", str(over["albedo"])]
+    if "density" in over:
+        cmd += ["--density", str(over["density"])]
+    return run_tool(cmd, 420)
 
 
 if __name__ == "__main__":

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <mutex>
 #include <new>
 #include <algorithm>
 #include <vector>
@@ -46,6 +48,32 @@ void dev_free(T*& p)
     if (p) cudaFree((void*)p);
     p = nullptr;
 }
+// a device temporary that is freed on every exit path (device out-of-memory is the EXPECTED failure of a large upload)
+struct DevTmp
+{
+    void* p = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+    ~DevTmp() { release(); }
+    cudaError_t alloc(size_t bytes)
+    {
+        release();
+        return cudaMalloc(&p, bytes ? bytes : 1);
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+bool env_flag(const char* name)
+{
+    const char* v = getenv(name);
+    return v && atoi(v) != 0;
+}
 }  // namespace
 
 struct vp_context
@@ -61,7 +89,9 @@ struct vp_context
     void*     octets      = nullptr;
     float2*   bounds_voxel = nullptr;
     float2*   bounds_cell = nullptr;
-    float*    opacity     = nullptr;
+    float*    opacity     = nullptr;  // bit-faithful apron table (parity)
+    void*     opacity_oct = nullptr;  // fp16 octets (production renderers)
+    float     opacity_ms  = 0.0f;     // device time of the last vp_precompute_opacity
     float*    sun_clear   = nullptr;
     uint32_t* bounds_half = nullptr;     // half-precision copies for the production renderers (coarse cells only)
     uint16_t* sun_clear_half = nullptr;
@@ -81,10 +111,15 @@ struct vp_context
     bool      have_volume = false;
     // instrumentation
     unsigned long long* d_stats = nullptr;
-    // work-pool counters of the production renderers, one per launch in flight: slots 0..7 belong to the overlap ring of
-    // the render_kernel shim (below), 8..11 rotate over launches on caller-given streams
+    // work-pool counters of the production renderers, one per launch in flight.  Slots rotate; each remembers the stream
+    // of its last launch and an event recorded behind it, and a launch on ANOTHER stream first waits for that event
+    // (cudaStreamWaitEvent): any number of caller streams is safe, launch n + kWorkSlots merely queues behind launch n.
+    static constexpr int kWorkSlots = 16;
     unsigned long long* d_work  = nullptr;
     unsigned            work_rr = 0;
+    cudaEvent_t         work_done[kWorkSlots] = {};
+    cudaStream_t        work_stream[kWorkSlots] = {};
+    bool                work_used[kWorkSlots] = {};
     // render_kernel shim, VP_MODE_FAST: consecutive one-frame launches go round-robin to four internal BLOCKING streams, so
     // the long tail of frame n (its last few paths) overlaps the bulk of frame n + 1 whenever the host does not
     // synchronise in between; blocking streams keep the legacy default-stream ordering the reference host relies on
@@ -96,6 +131,8 @@ struct vp_context
     cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
     bool                timed = false;
     float               inv_model[12];
+    void*               nccl_comm = nullptr;  // ncclComm_t of vp_nccl_init (one per context = per GPU)
+    int                 nccl_rank = -1, nccl_ranks = 0;
 };
 
 static void scene_defaults(Scene& S)
@@ -123,6 +160,8 @@ static void free_volume(vp_context* c)
     dev_free(c->bounds_voxel);
     dev_free(c->bounds_cell);
     dev_free(c->opacity);
+    dev_free(c->opacity_oct);
+    c->S.opacity_oct = nullptr;
     dev_free(c->sun_clear);
     c->S.sun_clear = nullptr;
     dev_free(c->bounds_half);
@@ -209,12 +248,16 @@ static int update_env_sampling(vp_context* c)
     S.env_pdfnorm_alt     = (float)w * (float)h * k1TwoPiPi / lumsum;
     for (int y = 0; y < h; y++) row_sum[y] = build_cdf_1d(lum.data() + (size_t)y * w, cdf_x.data() + (size_t)y * w, w);
     build_cdf_1d(row_sum.data(), cdf_y.data(), h);
+    DevTmp nx_, ny_;
+    VP_CUDA(nx_.alloc(total * sizeof(float)));
+    VP_CUDA(ny_.alloc((size_t)h * sizeof(float)));
+    VP_CUDA(cudaMemcpy(nx_.p, cdf_x.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    VP_CUDA(cudaMemcpy(ny_.p, cdf_y.data(), (size_t)h * sizeof(float), cudaMemcpyHostToDevice));
+    VP_CUDA(cudaDeviceSynchronize());
     dev_free(c->env_cdf_x);
     dev_free(c->env_cdf_y);
-    VP_CUDA(cudaMalloc(&c->env_cdf_x, total * sizeof(float)));
-    VP_CUDA(cudaMalloc(&c->env_cdf_y, (size_t)h * sizeof(float)));
-    VP_CUDA(cudaMemcpy(c->env_cdf_x, cdf_x.data(), total * sizeof(float), cudaMemcpyHostToDevice));
-    VP_CUDA(cudaMemcpy(c->env_cdf_y, cdf_y.data(), (size_t)h * sizeof(float), cudaMemcpyHostToDevice));
+    c->env_cdf_x = nx_.as<float>(); nx_.p = nullptr;
+    c->env_cdf_y = ny_.as<float>(); ny_.p = nullptr;
     S.env_cdf_x = c->env_cdf_x;
     S.env_cdf_y = c->env_cdf_y;
     S.env_mis   = 1;
@@ -227,12 +270,16 @@ static int update_sun_clear(vp_context* c)
     Scene& S = c->S;
     if (!c->have_volume || S.julia || !c->bounds_cell) return VP_OK;
     const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
+    VP_CUDA(cudaDeviceSynchronize());  // renders on caller streams may still be reading the tables rewritten below
     if (!c->sun_clear) VP_CUDA(cudaMalloc(&c->sun_clear, cells * sizeof(float)));
     const float cell = (float)(1 << S.cell_log2);
     const float wx = cell / S.vs_scale.x, wy = cell / S.vs_scale.y, wz = cell / S.vs_scale.z;  // world cell extents
     const float step = 0.5f * fminf(wx, fminf(wy, wz));
     S.sun_clear    = nullptr;
-    VP_CUDA(launch_sun_clear(S, S.sun_dir, step, c->sun_clear, 0));
+    // neighbour rings a vacuum sample needs on top of its own +-D window (see k_sun_clear): 0 except on tiny grids
+    const float need_vox = 0.75f * cell + 1.0f;
+    const int   ring     = (float)c->bound_D >= need_vox ? 0 : (int)ceilf((need_vox - (float)c->bound_D) / cell);
+    VP_CUDA(launch_sun_clear(S, S.sun_dir, step, ring, c->sun_clear, 0));
     c->launches++;
     VP_CUDA(cudaDeviceSynchronize());
     S.sun_clear    = c->sun_clear;
@@ -255,8 +302,10 @@ static int update_sun_clear(vp_context* c)
     return VP_OK;
 }
 
-// dense fp32 value volume on the device -> octet store + bound grids
-static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_voxel, int bounds_flags, int keep_dense)
+// dense fp32 value volume on the device -> bound grids + octet store.  Order matters for the peak footprint: the
+// per-voxel bound sweeps need the dense copy plus two float2 volumes (C2: 26 + 2 x 53 GB), the octet pool (54 GB) is
+// allocated only after their temporary is gone, so that even the parity-capable context of the full C2 grid fits 180 GB.
+static int build_from_dense_impl(vp_context* c, int nx, int ny, int nz, int store_voxel, int bounds_flags, int keep_dense)
 {
     Scene& S = c->S;
     S.nx = nx; S.ny = ny; S.nz = nz;
@@ -265,35 +314,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     const size_t nb = (size_t)S.nbx * S.nby * S.nbz;
     c->n_bricks     = nb;
 
-    // 1. brick classification + exclusive scan -> slots
-    uint32_t *flags = nullptr, *scan = nullptr;
-    void*     tmp   = nullptr;
-    size_t    tmp_bytes = 0;
-    VP_CUDA(cudaMalloc(&flags, nb * 4));
-    VP_CUDA(cudaMalloc(&scan, nb * 4));
-    VP_CUDA(launch_classify_bricks(c->dense, nx, ny, nz, S.nbx, S.nby, S.nbz, flags, 0));
-    VP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, scan, (int)nb, 0));
-    VP_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    VP_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, scan, (int)nb, 0));
-    uint32_t last_scan = 0, last_flag = 0;
-    VP_CUDA(cudaMemcpy(&last_scan, scan + nb - 1, 4, cudaMemcpyDeviceToHost));
-    VP_CUDA(cudaMemcpy(&last_flag, flags + nb - 1, 4, cudaMemcpyDeviceToHost));
-    c->n_slots = last_scan + last_flag;
-    VP_CUDA(cudaMalloc(&c->words, ((nb + 31) / 32) * sizeof(uint2)));
-    VP_CUDA(cudaMalloc(&c->slot_brick, (size_t)(c->n_slots ? c->n_slots : 1) * 4));
-    if (nb * 4 <= (size_t)4 << 20) VP_CUDA(cudaMalloc(&c->table, nb * 4));  // <= 4 MB: stays cache-resident
-    VP_CUDA(launch_make_words(flags, scan, nb, c->words, c->slot_brick, c->table, 0));
-    cudaFree(tmp);
-    cudaFree(flags);
-    cudaFree(scan);
-
-    // 2. octet pool
-    const size_t ob = store_voxel == kF32 ? 32 : (store_voxel == kF16 ? 16 : 8);
-    c->octet_bytes  = (size_t)c->n_slots * kBrickCells * ob;
-    VP_CUDA(cudaMalloc(&c->octets, c->octet_bytes ? c->octet_bytes : 32));
-    VP_CUDA(launch_fill_octets(c->dense, nx, ny, nz, S.nbx, S.nby, c->slot_brick, c->n_slots, c->octets, store_voxel, 0));
-
-    // 3. bounds.  D as the reference computes it (H.cpp:1098-1101)
+    // 1. bounds.  D as the reference computes it (H.cpp:1098-1101)
     float cell_size = 2.0f / (float)nx;
     int   D         = (int)ceil(kSearchRadius / cell_size);
     c->bound_D      = D;
@@ -304,7 +325,7 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     // up to 128 Mi voxels (1 GiB of bounds) the fast renderer simply uses the reference's own per-voxel windows: the
     // reference estimator is biased by construction and its expectation moves with the window
     if ((bounds_flags & VP_BOUNDS_EXACT) || N <= ((size_t)128 << 20)) cl = 0;
-    if (const char* f = getenv("VOLPATH_FORCE_CELL_LOG2")) cl = atoi(f) < 0 ? 0 : (atoi(f) > 3 ? 3 : atoi(f));  // experiments only
+    if (const char* f = getenv("VOLPATH_FORCE_CELL_LOG2")) cl = atoi(f) < 0 ? 0 : (atoi(f) > 3 ? 3 : atoi(f));  // tests / experiments
     const int cell = 1 << cl;
     S.cell_log2    = cl;
     S.ncx = (nx + cell - 1) >> cl; S.ncy = (ny + cell - 1) >> cl; S.ncz = (nz + cell - 1) >> cl;
@@ -312,14 +333,13 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     S.cs_off   = make_float3(S.vs_off.x / cell, S.vs_off.y / cell, S.vs_off.z / cell);
     if (bounds_flags & VP_BOUNDS_VOXEL)
     {
-        float2* t0 = nullptr;
+        DevTmp t0;
         VP_CUDA(cudaMalloc(&c->bounds_voxel, N * sizeof(float2)));
-        VP_CUDA(cudaMalloc(&t0, N * sizeof(float2)));
+        VP_CUDA(t0.alloc(N * sizeof(float2)));
         VP_CUDA(launch_bounds_axis_f32(c->dense, c->bounds_voxel, nx, ny, nz, 0, D, 1, 0));
-        VP_CUDA(launch_bounds_axis(c->bounds_voxel, t0, nx, ny, nz, 1, D, 1, 0));
-        VP_CUDA(launch_bounds_axis(t0, c->bounds_voxel, nx, ny, nz, 2, D, 1, 0));
+        VP_CUDA(launch_bounds_axis(c->bounds_voxel, t0.as<float2>(), nx, ny, nz, 1, D, 1, 0));
+        VP_CUDA(launch_bounds_axis(t0.as<float2>(), c->bounds_voxel, nx, ny, nz, 2, D, 1, 0));
         VP_CUDA(cudaDeviceSynchronize());
-        cudaFree(t0);
     }
     if ((bounds_flags & VP_BOUNDS_CELL) && cell == 1)
     {
@@ -329,36 +349,76 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
             VP_CUDA(cudaMemcpy(c->bounds_cell, c->bounds_voxel, N * sizeof(float2), cudaMemcpyDeviceToDevice));
         else
         {
-            float2* t0 = nullptr;
-            VP_CUDA(cudaMalloc(&t0, N * sizeof(float2)));
+            DevTmp t0;
+            VP_CUDA(t0.alloc(N * sizeof(float2)));
             VP_CUDA(launch_bounds_axis_f32(c->dense, c->bounds_cell, nx, ny, nz, 0, D, 1, 0));
-            VP_CUDA(launch_bounds_axis(c->bounds_cell, t0, nx, ny, nz, 1, D, 1, 0));
-            VP_CUDA(launch_bounds_axis(t0, c->bounds_cell, nx, ny, nz, 2, D, 1, 0));
+            VP_CUDA(launch_bounds_axis(c->bounds_cell, t0.as<float2>(), nx, ny, nz, 1, D, 1, 0));
+            VP_CUDA(launch_bounds_axis(t0.as<float2>(), c->bounds_cell, nx, ny, nz, 2, D, 1, 0));
             VP_CUDA(cudaDeviceSynchronize());
-            cudaFree(t0);
         }
     }
     else if (bounds_flags & VP_BOUNDS_CELL)
     {
-        float2 *t0 = nullptr, *t1 = nullptr;
-        VP_CUDA(cudaMalloc(&t0, (size_t)S.ncx * ny * nz * sizeof(float2)));
-        VP_CUDA(cudaMalloc(&t1, (size_t)S.ncx * S.ncy * nz * sizeof(float2)));
+        DevTmp t0, t1;
+        VP_CUDA(t0.alloc((size_t)S.ncx * ny * nz * sizeof(float2)));
+        VP_CUDA(t1.alloc((size_t)S.ncx * S.ncy * nz * sizeof(float2)));
         VP_CUDA(cudaMalloc(&c->bounds_cell, (size_t)S.ncx * S.ncy * S.ncz * sizeof(float2)));
-        VP_CUDA(launch_bounds_axis_f32(c->dense, t0, nx, ny, nz, 0, D, cell, 0));
-        VP_CUDA(launch_bounds_axis(t0, t1, S.ncx, ny, nz, 1, D, cell, 0));
-        VP_CUDA(launch_bounds_axis(t1, c->bounds_cell, S.ncx, S.ncy, nz, 2, D, cell, 0));
+        VP_CUDA(launch_bounds_axis_f32(c->dense, t0.as<float2>(), nx, ny, nz, 0, D, cell, 0));
+        VP_CUDA(launch_bounds_axis(t0.as<float2>(), t1.as<float2>(), S.ncx, ny, nz, 1, D, cell, 0));
+        VP_CUDA(launch_bounds_axis(t1.as<float2>(), c->bounds_cell, S.ncx, S.ncy, nz, 2, D, cell, 0));
+        // values: the reference's window of the cell's centre voxel; vacuum classification: the union window above
+        // (k_merge_cell_bounds; VOLPATH_UNION_WINDOWS=1 keeps the union values, for the bias measurement in DESIGN.md)
+        if (!env_flag("VOLPATH_UNION_WINDOWS"))
+        {
+            DevTmp cb;
+            const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
+            VP_CUDA(cb.alloc(cells * sizeof(float2)));
+            VP_CUDA(launch_bounds_axis_f32(c->dense, t0.as<float2>(), nx, ny, nz, 0, D, cell, 0, 1));
+            VP_CUDA(launch_bounds_axis(t0.as<float2>(), t1.as<float2>(), S.ncx, ny, nz, 1, D, cell, 0, 1));
+            VP_CUDA(launch_bounds_axis(t1.as<float2>(), cb.as<float2>(), S.ncx, S.ncy, nz, 2, D, cell, 0, 1));
+            VP_CUDA(launch_merge_cell_bounds(c->bounds_cell, cb.as<float2>(), cells, 0));
+            VP_CUDA(cudaDeviceSynchronize());
+        }
         VP_CUDA(cudaDeviceSynchronize());
-        cudaFree(t0);
-        cudaFree(t1);
     }
+    VP_CUDA(cudaDeviceSynchronize());
+
+    // 2. brick classification + exclusive scan -> slots
+    {
+        DevTmp flags, scan, tmp;
+        size_t tmp_bytes = 0;
+        VP_CUDA(flags.alloc(nb * 4));
+        VP_CUDA(scan.alloc(nb * 4));
+        VP_CUDA(launch_classify_bricks(c->dense, nx, ny, nz, S.nbx, S.nby, S.nbz, flags.as<uint32_t>(), 0));
+        VP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags.as<uint32_t>(), scan.as<uint32_t>(), (int)nb, 0));
+        VP_CUDA(tmp.alloc(tmp_bytes));
+        VP_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, flags.as<uint32_t>(), scan.as<uint32_t>(), (int)nb, 0));
+        uint32_t last_scan = 0, last_flag = 0;
+        VP_CUDA(cudaMemcpy(&last_scan, scan.as<uint32_t>() + nb - 1, 4, cudaMemcpyDeviceToHost));
+        VP_CUDA(cudaMemcpy(&last_flag, flags.as<uint32_t>() + nb - 1, 4, cudaMemcpyDeviceToHost));
+        c->n_slots = last_scan + last_flag;
+        VP_CUDA(cudaMalloc(&c->words, ((nb + 31) / 32) * sizeof(uint2)));
+        VP_CUDA(cudaMalloc(&c->slot_brick, (size_t)(c->n_slots ? c->n_slots : 1) * 4));
+        // <= 4 MB of flat table stays cache-resident; larger grids (and VOLPATH_FORCE_RANK_DIR=1, which lets the tests
+        // put small volumes on the large-volume path) look slots up in the rank directory
+        if (nb * 4 <= (size_t)4 << 20 && !env_flag("VOLPATH_FORCE_RANK_DIR")) VP_CUDA(cudaMalloc(&c->table, nb * 4));
+        VP_CUDA(launch_make_words(flags.as<uint32_t>(), scan.as<uint32_t>(), nb, c->words, c->slot_brick, c->table, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+    }
+
+    // 3. octet pool
+    const size_t ob = store_voxel == kF32 ? 32 : (store_voxel == kF16 ? 16 : 8);
+    c->octet_bytes  = (size_t)c->n_slots * kBrickCells * ob;
+    VP_CUDA(cudaMalloc(&c->octets, c->octet_bytes ? c->octet_bytes : 32));
+    VP_CUDA(launch_fill_octets(c->dense, nx, ny, nz, S.nbx, S.nby, c->slot_brick, c->n_slots, c->octets, store_voxel, 0));
     VP_CUDA(cudaDeviceSynchronize());
     if (!keep_dense) dev_free(c->dense);
     if (c->bounds_cell)
     {
         // vacuum jump distances (breadth-first dilation over the bound cells, up to 63 cells)
         const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
-        uint8_t*     tmp   = nullptr;
-        VP_CUDA(cudaMalloc(&tmp, cells));
+        DevTmp       tmp;
+        VP_CUDA(tmp.alloc(cells));
         // world sizes: a voxel per axis, the smallest cell edge, what the +-D window covers at least, and what a 0.05
         // segment plus the trilinear footprint (and a voxel of slack) needs; the deficit becomes the fringe margin
         const float vx = 1.0f / S.vs_scale.x, vy = 1.0f / S.vs_scale.y, vz = 1.0f / S.vs_scale.z;
@@ -371,13 +431,12 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         // breadth-first depth: 63 cells, fewer on very fine grids (each level is a pass over all cells)
         const int kmax = cells > ((size_t)1 << 30) ? 3 : (cells > ((size_t)160 << 20) ? 15 : 63);
         if (margin > kmax - 1) margin = kmax - 1;
-        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp, S.ncx, S.ncy, S.ncz, kmax, margin, cw, 0));
+        VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp.as<uint8_t>(), S.ncx, S.ncy, S.ncz, kmax, margin, cw, 0));
         VP_CUDA(cudaDeviceSynchronize());
-        cudaFree(tmp);
     }
 
     // coarse cells = a volume too large for per-voxel windows: keep the per-cell tables L2-resident in half precision
-    // (VOLPATH_HALF_TABLES=0/1 overrides the choice, for measurements)
+    // (VOLPATH_HALF_TABLES=0/1 overrides the choice, for measurements and tests)
     S.bounds_half = nullptr;
     {
         const char* ov   = getenv("VOLPATH_HALF_TABLES");
@@ -386,16 +445,16 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
         {
             const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
             // the copies are an optimisation: out of memory or values beyond the half range -> stay with the float tables
-            int *d_over = nullptr, h_over = 1;
-            if (cudaMalloc(&d_over, sizeof(int)) == cudaSuccess && cudaMalloc(&c->bounds_half, cells * sizeof(uint32_t)) == cudaSuccess &&
-                cudaMemset(d_over, 0, sizeof(int)) == cudaSuccess &&
-                launch_pack_bounds_half(c->bounds_cell, c->bounds_half, cells, d_over, 0) == cudaSuccess)
+            DevTmp d_over;
+            int    h_over = 1;
+            if (d_over.alloc(sizeof(int)) == cudaSuccess && cudaMalloc(&c->bounds_half, cells * sizeof(uint32_t)) == cudaSuccess &&
+                cudaMemset(d_over.p, 0, sizeof(int)) == cudaSuccess &&
+                launch_pack_bounds_half(c->bounds_cell, c->bounds_half, cells, d_over.as<int>(), 0) == cudaSuccess)
             {
                 c->launches++;
-                if (cudaMemcpy(&h_over, d_over, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) h_over = 1;
+                if (cudaMemcpy(&h_over, d_over.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) h_over = 1;
             }
             cudaGetLastError();
-            if (d_over) cudaFree(d_over);
             if (h_over) dev_free(c->bounds_half);
             S.bounds_half = c->bounds_half;
         }
@@ -417,11 +476,45 @@ static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_vox
     }
     return update_sun_clear(c);
 }
+static int build_from_dense(vp_context* c, int nx, int ny, int nz, int store_voxel, int bounds_flags, int keep_dense)
+{
+    const int rc = build_from_dense_impl(c, nx, ny, nz, store_voxel, bounds_flags, keep_dense);
+    if (rc != VP_OK)
+    {
+        cudaGetLastError();
+        free_volume(c);  // a failed build leaves no half-initialised volume behind
+    }
+    return rc;
+}
 
 extern "C" {
 
+int vp_destroy(vp_context* c);
 const char* vp_last_error(void) { return g_err; }
 const char* vp_version(void) { return "volpath-b200 0.1 (sm_100a)"; }
+
+static int create_impl(vp_context* c, int device)
+{
+    c->device = device;
+    cudaDeviceProp prop;
+    VP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    set_build_sm_count(c->num_sms);
+    scene_defaults(c->S);
+    const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    memcpy(c->inv_model, id, sizeof(id));
+    VP_CUDA(cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
+    VP_CUDA(cudaMalloc(&c->d_work, vp_context::kWorkSlots * sizeof(unsigned long long)));
+    for (cudaEvent_t& e : c->work_done) VP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    VP_CUDA(cudaEventCreate(&c->ev0));
+    VP_CUDA(cudaEventCreate(&c->ev1));
+    // a 1x1 black environment until init_envmap is called
+    VP_CUDA(cudaMalloc(&c->env, sizeof(float4)));
+    VP_CUDA(cudaMemset(c->env, 0, sizeof(float4)));
+    c->S.env = c->env; c->S.env_w = 1; c->S.env_h = 1;
+    return VP_OK;
+}
 
 int vp_create(int device, vp_context** out)
 {
@@ -432,30 +525,22 @@ int vp_create(int device, vp_context** out)
     VP_CUDA(cudaSetDevice(device));
     vp_context* c = new (std::nothrow) vp_context();
     if (!c) return fail(VP_ERR_INVALID, "vp_create: out of host memory");
-    c->device = device;
-    cudaDeviceProp prop;
-    VP_CUDA(cudaGetDeviceProperties(&prop, device));
-    c->num_sms = prop.multiProcessorCount;
-    scene_defaults(c->S);
-    const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    memcpy(c->inv_model, id, sizeof(id));
-    VP_CUDA(cudaMalloc(&c->d_stats, 16 * sizeof(unsigned long long)));
-    VP_CUDA(cudaMemset(c->d_stats, 0, 16 * sizeof(unsigned long long)));
-    VP_CUDA(cudaMalloc(&c->d_work, 12 * sizeof(unsigned long long)));
-    VP_CUDA(cudaEventCreate(&c->ev0));
-    VP_CUDA(cudaEventCreate(&c->ev1));
-    // a 1x1 black environment until init_envmap is called
-    VP_CUDA(cudaMalloc(&c->env, sizeof(float4)));
-    VP_CUDA(cudaMemset(c->env, 0, sizeof(float4)));
-    c->S.env = c->env; c->S.env_w = 1; c->S.env_h = 1;
+    const int rc = create_impl(c, device);
+    if (rc != VP_OK)
+    {
+        vp_destroy(c);  // frees whatever was allocated; g_err keeps the first failure
+        return rc;
+    }
     *out = c;
     return VP_OK;
 }
 
+int vp_nccl_destroy(vp_context* c);
 int vp_destroy(vp_context* c)
 {
     if (!c) return VP_OK;
     cudaSetDevice(c->device);
+    vp_nccl_destroy(c);
     free_volume(c);
     dev_free(c->env);
     dev_free(c->env_cdf_x);
@@ -464,6 +549,8 @@ int vp_destroy(vp_context* c)
     dev_free(c->d_work);
     for (cudaStream_t& r : c->ring)
         if (r) cudaStreamDestroy(r);
+    for (cudaEvent_t& e : c->work_done)
+        if (e) cudaEventDestroy(e);
     dev_free(c->host_acc);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -500,12 +587,11 @@ int vp_upload_volume(vp_context* c, const void* volume, int nx, int ny, int nz, 
     }
     else
     {
-        uint8_t* d8 = nullptr;
-        VP_CUDA(cudaMalloc(&d8, N));
-        VP_CUDA(cudaMemcpy(d8, volume, N, kind));
-        VP_CUDA(launch_u8_to_f32(d8, c->dense, N, 0));
+        DevTmp d8;
+        VP_CUDA(d8.alloc(N));
+        VP_CUDA(cudaMemcpy(d8.p, volume, N, kind));
+        VP_CUDA(launch_u8_to_f32(d8.as<uint8_t>(), c->dense, N, 0));
         VP_CUDA(cudaDeviceSynchronize());
-        cudaFree(d8);
     }
     set_box(c, nx, ny, nz, boxmin3, boxmax3);
     return build_from_dense(c, nx, ny, nz, store_voxel, bounds_flags, 0);
@@ -560,9 +646,14 @@ int vp_set_envmap(vp_context* c, const float* rgba, int width, int height)
 {
     if (!c || !rgba || width < 1 || height < 1) return fail(VP_ERR_INVALID, "vp_set_envmap: bad arguments");
     VP_CUDA(cudaSetDevice(c->device));
+    // allocate the new map first and swap it in on success: a failed upload leaves the old map in use
+    DevTmp fresh;
+    VP_CUDA(fresh.alloc((size_t)width * height * sizeof(float4)));
+    VP_CUDA(cudaMemcpy(fresh.p, rgba, (size_t)width * height * sizeof(float4), cudaMemcpyHostToDevice));
+    VP_CUDA(cudaDeviceSynchronize());  // no render may still be reading the old map when it is freed
     dev_free(c->env);
-    VP_CUDA(cudaMalloc(&c->env, (size_t)width * height * sizeof(float4)));
-    VP_CUDA(cudaMemcpy(c->env, rgba, (size_t)width * height * sizeof(float4), cudaMemcpyHostToDevice));
+    c->env  = fresh.as<float4>();
+    fresh.p = nullptr;
     c->S.env = c->env; c->S.env_w = width; c->S.env_h = height;
     c->env_host.assign(rgba, rgba + (size_t)width * height * 4);
     c->env_host_stale = false;
@@ -575,8 +666,13 @@ int vp_bake_sunsky(vp_context* c, const vp_sky_state* st, int width, int height)
     VP_CUDA(cudaSetDevice(c->device));
     if (!c->env || c->S.env_w != width || c->S.env_h != height)
     {
+        DevTmp fresh;
+        VP_CUDA(fresh.alloc((size_t)width * height * sizeof(float4)));
+        VP_CUDA(cudaDeviceSynchronize());
         dev_free(c->env);
-        VP_CUDA(cudaMalloc(&c->env, (size_t)width * height * sizeof(float4)));
+        c->env  = fresh.as<float4>();
+        fresh.p = nullptr;
+        c->S.env = c->env; c->S.env_w = width; c->S.env_h = height;
     }
     VP_CUDA(launch_bake_sunsky(*st, c->env, width, height, 0));
     c->launches++;
@@ -642,26 +738,65 @@ int vp_precompute_opacity(vp_context* c, const float* dir3)
     if (!c->have_volume) return fail(VP_ERR_NO_VOLUME, "vp_precompute_opacity: no volume");
     VP_CUDA(cudaSetDevice(c->device));
     if (c->S.julia) return VP_OK;  // the table of the no-OpenVDB build is built from a zero density
+    VP_CUDA(cudaDeviceSynchronize());
     dev_free(c->opacity);
+    dev_free(c->opacity_oct);
     c->S.have_opacity = 0;
     c->S.opacity      = nullptr;
-    VP_CUDA(cudaMalloc(&c->opacity, (size_t)(c->n_slots ? c->n_slots : 1) * kOpBrickPad * sizeof(float)));
-    VP_CUDA(launch_precompute_opacity(c->S, c->slot_brick, c->n_slots, c->opacity, make_float3(dir3[0], dir3[1], dir3[2]), 0));
-    c->launches++;
-    VP_CUDA(cudaDeviceSynchronize());
+    c->S.opacity_oct  = nullptr;
+    const float3 dir  = make_float3(dir3[0], dir3[1], dir3[2]);
+    const size_t slots = c->n_slots ? c->n_slots : 1;
+    cudaEvent_t  t0 = nullptr, t1 = nullptr;
+    VP_CUDA(cudaEventCreate(&t0));
+    VP_CUDA(cudaEventCreate(&t1));
+    cudaEventRecord(t0, 0);
+    int rc = VP_OK;
+    // (1) the bit-faithful per-voxel march (K.cu:483-524) for VP_MODE_PARITY: only contexts that can run that mode
+    //     (VP_BOUNDS_VOXEL) pay for it; VOLPATH_OPACITY_FAITHFUL=1 forces it (tests compare the two tables)
+    if (c->bounds_voxel || env_flag("VOLPATH_OPACITY_FAITHFUL"))
+    {
+        cudaError_t e = cudaMalloc(&c->opacity, slots * kOpBrickPad * sizeof(float));
+        if (e == cudaSuccess) e = launch_precompute_opacity(c->S, c->slot_brick, c->n_slots, c->opacity, dir, 0);
+        if (e != cudaSuccess) rc = fail((int)e, "vp_precompute_opacity (per-voxel march): %s", cudaGetErrorString(e));
+        c->launches++;
+    }
+    // (2) the production table: swept build, fp16 octets (volpath_build.cu)
+    if (rc == VP_OK && c->bounds_cell)
+    {
+        int K = 64;
+        if (const char* k = getenv("VOLPATH_OPACITY_K")) K = atoi(k) > 0 ? atoi(k) : K;
+        cudaError_t e = cudaMalloc(&c->opacity_oct, slots * kBrickCells * 16);
+        if (e == cudaSuccess) e = launch_opacity_octets(c->S, c->slot_brick, c->n_slots, c->opacity_oct, dir, K, 0);
+        if (e != cudaSuccess) rc = fail((int)e, "vp_precompute_opacity (swept octets): %s", cudaGetErrorString(e));
+        c->launches += 2;
+    }
+    cudaEventRecord(t1, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc == VP_OK && e != cudaSuccess) rc = fail((int)e, "vp_precompute_opacity: %s", cudaGetErrorString(e));
+    if (rc == VP_OK) cudaEventElapsedTime(&c->opacity_ms, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (rc != VP_OK)
+    {
+        cudaGetLastError();
+        dev_free(c->opacity);
+        dev_free(c->opacity_oct);
+        return rc;
+    }
     c->S.opacity      = c->opacity;
-    c->S.have_opacity = 1;
+    c->S.have_opacity = c->opacity ? 1 : 0;
+    c->S.opacity_oct  = c->opacity_oct;
     return VP_OK;
 }
 
 static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
-                     cudaStream_t st, unsigned long long* d_work);
+                     cudaStream_t st);
 
 int vp_render(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
               vp_stream stream)
 {
     if (!c) return fail(VP_ERR_INVALID, "vp_render: bad arguments");
-    return render_on(c, d_sum, first_frame, n_frames, frame_stride, p, mode, (cudaStream_t)stream, c->d_work + 8 + (c->work_rr++ & 3u));
+    return render_on(c, d_sum, first_frame, n_frames, frame_stride, p, mode, (cudaStream_t)stream);
 }
 
 // the render_kernel shim's launch: see vp_context::ring
@@ -673,11 +808,11 @@ static int render_shim(vp_context* c, void* d_sum, int frame, const vp_param* p,
     static const unsigned n_ring = getenv("VOLPATH_SHIM_STREAMS") ? (unsigned)std::min(8, std::max(1, atoi(getenv("VOLPATH_SHIM_STREAMS")))) : 4u;
     const unsigned slot = c->ring_rr++ % n_ring;
     if (!c->ring[slot]) VP_CUDA(cudaStreamCreate(&c->ring[slot]));
-    return render_on(c, d_sum, frame, 1, 1, p, mode, c->ring[slot], c->d_work + slot);
+    return render_on(c, d_sum, frame, 1, 1, p, mode, c->ring[slot]);
 }
 
 static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
-                     cudaStream_t st, unsigned long long* d_work)
+                     cudaStream_t st)
 {
     if (!c || !d_sum || !p) return fail(VP_ERR_INVALID, "vp_render: bad arguments");
     if (!c->have_volume) return fail(VP_ERR_NO_VOLUME, "vp_render: no volume uploaded");
@@ -695,6 +830,10 @@ static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, 
     {
         if (c->S.env_mis && mode == VP_MODE_WAVE) return fail(VP_ERR_UNSUPPORTED, "vp_render: env-map sampling is not implemented in the wavefront form");
         if (!c->S.julia && !c->S.bounds_cell) return fail(VP_ERR_INVALID, "vp_render: fast mode needs VP_BOUNDS_CELL");
+        // this launch's work-pool counter (see vp_context::d_work)
+        const unsigned ws = c->work_rr++ % vp_context::kWorkSlots;
+        if (c->work_used[ws] && c->work_stream[ws] != st) VP_CUDA(cudaStreamWaitEvent(st, c->work_done[ws], 0));
+        unsigned long long* d_work = c->d_work + ws;
         // all frames of the call are ONE launch (one work pool), as long as tiles * frames fits 31 bits
         const long long tiles = (long long)((p->width + 7) / 8) * ((p->height + 3) / 4);
         long long       cap   = ((1ll << 31) - 1) / tiles;
@@ -710,6 +849,9 @@ static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, 
                                            c->stats_on ? c->d_stats : nullptr, c->num_sms, st));
             c->launches++;
         }
+        VP_CUDA(cudaEventRecord(c->work_done[ws], st));
+        c->work_stream[ws] = st;
+        c->work_used[ws]   = true;
     }
     else
         return fail(VP_ERR_INVALID, "vp_render: unknown mode %d", mode);
@@ -809,6 +951,22 @@ int vp_get_opacity(vp_context* c, float* h_out)
     VP_CUDA(e);
     return VP_OK;
 }
+int vp_get_opacity_fast(vp_context* c, float* h_out)
+{
+    if (!c || !c->opacity_oct) return fail(VP_ERR_INVALID, "no production opacity table");
+    size_t N = (size_t)c->S.nx * c->S.ny * c->S.nz;
+    DevTmp d;
+    VP_CUDA(d.alloc(N * sizeof(float)));
+    VP_CUDA(launch_gather_opacity_oct(c->S, d.as<float>(), 0));
+    VP_CUDA(cudaMemcpy(h_out, d.p, N * sizeof(float), cudaMemcpyDeviceToHost));
+    return VP_OK;
+}
+int vp_opacity_build_ms(vp_context* c, float* ms)
+{
+    if (!c || !ms) return fail(VP_ERR_INVALID, "bad arguments");
+    *ms = c->opacity_ms;
+    return VP_OK;
+}
 int vp_fetch_density(vp_context* c, const float* h_pos3, int n, int parity_filter, float* h_out)
 {
     if (!c || !c->have_volume || c->S.julia) return fail(VP_ERR_NO_VOLUME, "vp_fetch_density: no stored volume");
@@ -833,7 +991,8 @@ int vp_volume_stats(vp_context* c, unsigned long long* out8)
     out8[3] = (unsigned long long)c->bound_D;
     out8[4] = c->bounds_cell ? (unsigned long long)c->S.ncx * c->S.ncy * c->S.ncz * sizeof(float2) : 0;
     out8[5] = c->bounds_voxel ? (unsigned long long)c->S.nx * c->S.ny * c->S.nz * sizeof(float2) : 0;
-    out8[6] = c->opacity ? (unsigned long long)c->n_slots * kOpBrickPad * sizeof(float) : 0;
+    out8[6] = (c->opacity ? (unsigned long long)c->n_slots * kOpBrickPad * sizeof(float) : 0) +
+              (c->opacity_oct ? (unsigned long long)c->n_slots * kBrickCells * 16 : 0);
     out8[7] = (unsigned long long)(1u << c->S.cell_log2);
     return VP_OK;
 }
@@ -904,6 +1063,189 @@ int vp_dev_free(void* p) { return (int)cudaFree(p); }
 int vp_dev_zero(void* p, size_t bytes) { return (int)cudaMemset(p, 0, bytes); }
 int vp_dev_to_host(void* h, const void* d, size_t bytes) { return (int)cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost); }
 int vp_host_to_dev(void* d, const void* h, size_t bytes) { return (int)cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); }
+
+// =======================================================================================================
+// (3) combining the per-GPU float4 sums of a sample-sharded render: NCCL over NVLink / NVSwitch.
+// libnccl.so.2 is bound at run time (dlopen), so the library itself has no link-time dependency on it and a process
+// that already carries an NCCL (e.g. torch's) shares that copy.  The few NCCL types used are ABI-stable across 2.x
+// (nccl.h: ncclUniqueId = 128 opaque bytes, ncclComm_t = opaque pointer, ncclFloat = 7, ncclSum = 0, ncclSuccess = 0).
+// =======================================================================================================
+namespace
+{
+struct NcclId { char internal[128]; };
+struct NcclApi
+{
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*)                                                               = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int)                                             = nullptr;
+    int (*CommInitAll)(void**, int, const int*)                                               = nullptr;
+    int (*CommDestroy)(void*)                                                                 = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t)             = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t)               = nullptr;
+    int (*GroupStart)()                                                                       = nullptr;
+    int (*GroupEnd)()                                                                         = nullptr;
+    const char* (*GetErrorString)(int)                                                        = nullptr;
+    int (*GetVersion)(int*)                                                                   = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl()
+{
+    static NcclApi    api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("VOLPATH_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names)
+        {
+            if (!n || !*n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+#define VP_SYM(field, name) *(void**)(&api.field) = dlsym(api.lib, name)
+        VP_SYM(GetUniqueId, "ncclGetUniqueId");
+        VP_SYM(CommInitRank, "ncclCommInitRank");
+        VP_SYM(CommInitAll, "ncclCommInitAll");
+        VP_SYM(CommDestroy, "ncclCommDestroy");
+        VP_SYM(Reduce, "ncclReduce");
+        VP_SYM(AllReduce, "ncclAllReduce");
+        VP_SYM(GroupStart, "ncclGroupStart");
+        VP_SYM(GroupEnd, "ncclGroupEnd");
+        VP_SYM(GetErrorString, "ncclGetErrorString");
+        VP_SYM(GetVersion, "ncclGetVersion");
+#undef VP_SYM
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.Reduce && api.GroupStart &&
+                 api.GroupEnd && api.GetErrorString;
+    });
+    return api;
+}
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+#define VP_NCCL(x)                                                                                              \
+    do {                                                                                                        \
+        int r_ = (x);                                                                                           \
+        if (r_ != 0) return fail(20000 + r_, "%s: %s", #x, nccl().GetErrorString ? nccl().GetErrorString(r_) : "?"); \
+    } while (0)
+}  // namespace
+
+int vp_nccl_available(void)
+{
+    if (!nccl().ok) return 0;
+    int v = 0;
+    if (nccl().GetVersion) nccl().GetVersion(&v);
+    return v > 0 ? v : 1;
+}
+
+int vp_nccl_unique_id(char* out128)
+{
+    if (!out128) return fail(VP_ERR_INVALID, "vp_nccl_unique_id: null out");
+    if (!nccl().ok) return fail(VP_ERR_UNSUPPORTED, "vp_nccl_unique_id: libnccl.so.2 not found (set VOLPATH_NCCL_LIB)");
+    NcclId id;
+    VP_NCCL(nccl().GetUniqueId(&id));
+    memcpy(out128, id.internal, sizeof(id.internal));
+    return VP_OK;
+}
+
+int vp_nccl_init(vp_context* c, int n_ranks, int rank, const char* id128)
+{
+    if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(VP_ERR_INVALID, "vp_nccl_init: bad arguments");
+    if (!nccl().ok) return fail(VP_ERR_UNSUPPORTED, "vp_nccl_init: libnccl.so.2 not found (set VOLPATH_NCCL_LIB)");
+    VP_CUDA(cudaSetDevice(c->device));
+    vp_nccl_destroy(c);
+    NcclId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    VP_NCCL(nccl().CommInitRank(&c->nccl_comm, n_ranks, id, rank));
+    c->nccl_rank  = rank;
+    c->nccl_ranks = n_ranks;
+    return VP_OK;
+}
+
+int vp_nccl_destroy(vp_context* c)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    if (c->nccl_comm && nccl().ok)
+    {
+        cudaSetDevice(c->device);
+        nccl().CommDestroy(c->nccl_comm);
+    }
+    c->nccl_comm  = nullptr;
+    c->nccl_rank  = -1;
+    c->nccl_ranks = 0;
+    return VP_OK;
+}
+
+int vp_reduce_nccl(vp_context* c, const void* d_send, void* d_recv, int size, int root, vp_stream stream)
+{
+    if (!c || !d_send || size < 0) return fail(VP_ERR_INVALID, "vp_reduce_nccl: bad arguments");
+    if (!c->nccl_comm) return fail(VP_ERR_INVALID, "vp_reduce_nccl: vp_nccl_init has not been called on this context");
+    if (root < 0 || root >= c->nccl_ranks) return fail(VP_ERR_INVALID, "vp_reduce_nccl: root %d out of range", root);
+    if (c->nccl_rank == root && !d_recv) return fail(VP_ERR_INVALID, "vp_reduce_nccl: the root needs a receive buffer");
+    VP_CUDA(cudaSetDevice(c->device));
+    VP_NCCL(nccl().Reduce(d_send, d_recv, (size_t)size * 4, kNcclFloat, kNcclSum, root, c->nccl_comm, (cudaStream_t)stream));
+    c->launches++;
+    return VP_OK;
+}
+
+// single-process hosts: one context per GPU, all driven from this process; the sums are added into d_sums[root].
+// NCCL (one communicator per device, grouped ncclReduce) when it can be loaded, else peer copies + the add kernel.
+int vp_reduce(vp_context** ctxs, void** d_sums, int n, int size, int root)
+{
+    if (!ctxs || !d_sums || n < 1 || size < 0 || root < 0 || root >= n) return fail(VP_ERR_INVALID, "vp_reduce: bad arguments");
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i] || !d_sums[i]) return fail(VP_ERR_INVALID, "vp_reduce: null context or buffer %d", i);
+    if (n == 1) return VP_OK;
+    for (int i = 0; i < n; i++)
+    {
+        VP_CUDA(cudaSetDevice(ctxs[i]->device));
+        VP_CUDA(cudaDeviceSynchronize());
+    }
+    static std::vector<int>   cached_devs;
+    static std::vector<void*> cached_comms;
+    std::vector<int>          devs(n);
+    for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
+    const bool use_nccl = nccl().ok && !env_flag("VOLPATH_REDUCE_P2P");
+    if (use_nccl)
+    {
+        if (cached_devs != devs)
+        {
+            for (void* cm : cached_comms) nccl().CommDestroy(cm);
+            cached_comms.assign(n, nullptr);
+            cached_devs.clear();
+            VP_NCCL(nccl().CommInitAll(cached_comms.data(), n, devs.data()));
+            cached_devs = devs;
+        }
+        VP_NCCL(nccl().GroupStart());
+        for (int i = 0; i < n; i++)
+        {
+            cudaSetDevice(devs[i]);
+            int r = nccl().Reduce(d_sums[i], d_sums[root], (size_t)size * 4, kNcclFloat, kNcclSum, root, cached_comms[i], 0);
+            if (r != 0)
+            {
+                nccl().GroupEnd();
+                return fail(20000 + r, "ncclReduce: %s", nccl().GetErrorString(r));
+            }
+        }
+        VP_NCCL(nccl().GroupEnd());
+        for (int i = 0; i < n; i++)
+        {
+            VP_CUDA(cudaSetDevice(devs[i]));
+            VP_CUDA(cudaDeviceSynchronize());
+            ctxs[i]->launches++;
+        }
+        return VP_OK;
+    }
+    // no NCCL: stage each peer sum next to the root's and add it there
+    VP_CUDA(cudaSetDevice(devs[root]));
+    DevTmp stage;
+    VP_CUDA(stage.alloc((size_t)size * sizeof(float4)));
+    for (int i = 0; i < n; i++)
+    {
+        if (i == root) continue;
+        VP_CUDA(cudaMemcpyPeer(stage.p, devs[root], d_sums[i], devs[i], (size_t)size * sizeof(float4)));
+        VP_CUDA(launch_accumulate((float4*)d_sums[root], stage.as<float4>(), size, 0));
+        ctxs[root]->launches++;
+        VP_CUDA(cudaDeviceSynchronize());
+    }
+    return VP_OK;
+}
 
 // =======================================================================================================
 // (1) reference-named shims over one implicit context on the current device

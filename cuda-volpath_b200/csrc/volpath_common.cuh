@@ -47,7 +47,8 @@ struct Scene
     const float2*   bounds_voxel;  // [nz][ny][nx] (max,min)   -- parity
     const float2*   bounds_cell;   // [ncz][ncy][ncx] (max,min) -- fast; cell = (1 << cell_log2)^3 voxels
     int             cell_log2;
-    const float*    opacity;       // per brick slot: 9^3 floats (+pad)
+    const float*    opacity;       // per brick slot: 9^3 floats (+pad) -- the bit-faithful table VP_MODE_PARITY reads
+    const void*     opacity_oct;   // per cell: the 8 corner values as fp16 (16 B) -- what the production renderers read
     const float4*   env;           // [env_h][env_w]
     int             env_w, env_h;
     // env-map importance sampling (the reference's PASSIVE_ENVMAP 0 variant, K.cu:21): CDF rows + normalisation

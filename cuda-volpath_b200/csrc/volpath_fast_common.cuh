@@ -54,8 +54,9 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     return VT == kU8 ? r * (1.0f / 255.0f) : r;
 }
 
-// opacity table for the production renderers: same 9^3 apron blocks and trilinear weights as fetch_opacity (K.cu:541-542),
-// addressed like density_at (one FMA per axis, FMA lerps)
+// opacity table of the production renderers: the cell's 8 corner values sit in one 16-byte fp16 octet (same slot and
+// cell addressing as the density octets), so the lookup of K.cu:2183-2195 is one directory load + ONE vector load;
+// trilinear weights as the texture unit defines them (K.cu:541-542: always linear), FMA lerps
 template <int LY = 0>
 __device__ __forceinline__ float opacity_at(const Scene& S, float3 pos)
 {
@@ -65,11 +66,10 @@ __device__ __forceinline__ float opacity_at(const Scene& S, float3 pos)
     int   ix = clampi((int)fx, 0, S.nx), iy = clampi((int)fy, 0, S.ny), iz = clampi((int)fz, 0, S.nz);
     uint32_t slot = brick_slot<LY>(S, ix, iy, iz);
     if (slot == kEmptyBrick) return 0.0f;  // only reachable where the density is zero around pos
-    const float* q = S.opacity + (size_t)slot * kOpBrickPad + (((iz & (kBrick - 1)) * 9 + (iy & (kBrick - 1))) * 9 + (ix & (kBrick - 1)));
-    float v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 9), v3 = __ldg(q + 10);
-    float v4 = __ldg(q + 81), v5 = __ldg(q + 82), v6 = __ldg(q + 90), v7 = __ldg(q + 91);
+    float v[8];
+    load_octet<kF16>(S.opacity_oct, cell_in_slot(slot, ix, iy, iz), v);
     float a = xb - fx, b = yb - fy, g = zb - fz;
-    float c00 = fmaf(a, v1 - v0, v0), c10 = fmaf(a, v3 - v2, v2), c01 = fmaf(a, v5 - v4, v4), c11 = fmaf(a, v7 - v6, v6);
+    float c00 = fmaf(a, v[1] - v[0], v[0]), c10 = fmaf(a, v[3] - v[2], v[2]), c01 = fmaf(a, v[5] - v[4], v[4]), c11 = fmaf(a, v[7] - v[6], v[6]);
     float c0 = fmaf(b, c10 - c00, c00), c1 = fmaf(b, c11 - c01, c01);
     return fmaf(g, c1 - c0, c0);
 }

@@ -56,12 +56,18 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #ifndef VP_STEP_MINLANES
 #define VP_STEP_MINLANES 16
 #endif
+#ifndef VP_INLINE_SEG
+#define VP_INLINE_SEG 0
+#endif
+#ifndef VP_CHROMA_CTAS
+#define VP_CHROMA_CTAS 10
+#endif
 
 constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
 // chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 10 CTAs (48 registers); the MIS variant 8
 __host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis)
 {
-    return (mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > 10 ? 10 : kFastCtasPerSm))) * (128 / kFastThreads);
+    return (mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > VP_CHROMA_CTAS ? VP_CHROMA_CTAS : kFastCtasPerSm))) * (128 / kFastThreads);
 }
 constexpr uint32_t kFull         = 0xffffffffu;
 constexpr uint32_t kClaim        = 256;  // items per warp-level claim (large launches); small launches claim less, see launch_fast_t
@@ -382,6 +388,29 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     {
                         dist = lim;  // crossed the segment: tracking restart
                         st   = kModeSeg;
+#if VP_INLINE_SEG
+                        // The common continuation -- the next 0.05 segment has medium and no control component -- is set
+                        // up right here, so the lane keeps walking instead of waiting for a segment-block vote; exits,
+                        // vacuum (jump distances) and decomposition segments still go through the segment block.
+                        if (!JULIA && !STATS)
+                        {
+                            const float t_ex = t_exit;
+                            if (dist < t_ex)
+                            {
+                                const float2 bnd = bounds_at<LY>(S, pos);
+                                if (bnd.x > 0.0f && !(bnd.y > 0.0f))
+                                {
+                                    const float dmx = fmaxf(1e-4f, bnd.x);
+                                    dmax = dmx;
+                                    maj  = max_sig_t * dens * dmx;  // dens already belongs to the current scatter count
+                                    lim  = fminf(dist + kSearchRadius, t_ex);
+                                    sigc = 0.0f;
+                                    inv  = __fdividef(1.0f, maj);
+                                    st   = kModeStep;
+                                }
+                            }
+                        }
+#endif
                     }
                 }
                 else if (GRAY)
@@ -521,7 +550,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 if ((int)rng.frame > 10 && n > 20)  // K.cu:2183: precomputed sun opacity
                 {
                     if (STATS) c_op++;
-                    float  tau = (!JULIA && S.have_opacity) ? opacity_at<LY>(S, o) : 0.0f;
+                    float  tau = (!JULIA && S.opacity_oct) ? opacity_at<LY>(S, o) : 0.0f;
                     float3 a   = GRAY ? f3(__expf(-sig_t.x * dens * tau))
                                       : f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
                     L          = float3(L) + S.sun_power * ((GRAY ? f3(T.x) : T) * float(ph) * a);

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                 STF(F_DENS, dens);
                 if ((int)frame > 10 && n > 20)
                 {
-                    float  tau = (!JULIA && S.have_opacity) ? opacity_at(S, o) : 0.0f;
+                    float  tau = (!JULIA && S.opacity_oct) ? opacity_at(S, o) : 0.0f;
                     float3 a   = f3(__expf(-sig_t.x * dens * tau), __expf(-sig_t.y * dens * tau), __expf(-sig_t.z * dens * tau));
                     float3 L   = LD3(F_LX);
                     L          = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);

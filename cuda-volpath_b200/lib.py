@@ -68,10 +68,18 @@ SIGNATURES = {
     "vp_resolve": (c_int, [c_vp, c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float, c_vp]),
     "vp_accumulate": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     "vp_sync": (c_int, [c_vp]),
+    "vp_nccl_available": (c_int, []),
+    "vp_nccl_unique_id": (c_int, [ctypes.c_char_p]),
+    "vp_nccl_init": (c_int, [c_vp, c_int, c_int, ctypes.c_char_p]),
+    "vp_reduce_nccl": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "vp_nccl_destroy": (c_int, [c_vp]),
+    "vp_reduce": (c_int, [ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_int, c_int, c_int]),
     "vp_get_bounds_voxel": (c_int, [c_vp, c_fp]),
     "vp_get_bounds_cell": (c_int, [c_vp, c_fp, ctypes.POINTER(c_int)]),
     "vp_get_half_tables": (c_int, [c_vp, c_vp, c_vp, c_fp, ctypes.POINTER(c_int)]),
     "vp_get_opacity": (c_int, [c_vp, c_fp]),
+    "vp_get_opacity_fast": (c_int, [c_vp, c_fp]),
+    "vp_opacity_build_ms": (c_int, [c_vp, c_fp]),
     "vp_fetch_density": (c_int, [c_vp, c_fp, c_int, c_int, c_fp]),
     "vp_volume_stats": (c_int, [c_vp, c_u64p]),
     "vp_rng_sequence": (c_int, [c_vp, c_uint, c_uint, c_uint, c_int, c_fp, ctypes.POINTER(c_uint)]),

@@ -116,6 +116,24 @@ class Renderer:
     def sync(self):
         _l.check(self.L.vp_sync(self.h))
 
+    # ---- multi-GPU: the library's own NCCL reduce (include/volpath.h, "combining the per-GPU sums") -------------
+    def nccl_unique_id(self):
+        """128 opaque bytes from ncclGetUniqueId: created on one rank, distributed by the host's own means."""
+        buf = ctypes.create_string_buffer(128)
+        _l.check(self.L.vp_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_init(self, n_ranks, rank, unique_id):
+        assert len(unique_id) == 128
+        _l.check(self.L.vp_nccl_init(self.h, n_ranks, rank, unique_id))
+
+    def reduce_nccl(self, d_send_ptr, d_recv_ptr, size, root=0, stream=None):
+        """ncclReduce(sum) of `size` float4 onto rank `root` (d_recv_ptr may equal d_send_ptr; None off-root)."""
+        _l.check(self.L.vp_reduce_nccl(self.h, d_send_ptr, d_recv_ptr, size, root, stream))
+
+    def nccl_destroy(self):
+        _l.check(self.L.vp_nccl_destroy(self.h))
+
     # ---- introspection -----------------------------------------------------------------------------------
     def bounds_voxel(self):
         nx, ny, nz = self.dims
@@ -185,6 +203,18 @@ class Renderer:
         out = np.empty((nz, ny, nx), np.float32)
         _l.check(self.L.vp_get_opacity(self.h, _fp(out)))
         return out
+
+    def opacity_fast(self):
+        """The production renderers' table (swept build, fp16 octets) as a dense [nz, ny, nx] array."""
+        nx, ny, nz = self.dims
+        out = np.empty((nz, ny, nx), np.float32)
+        _l.check(self.L.vp_get_opacity_fast(self.h, _fp(out)))
+        return out
+
+    def opacity_build_ms(self):
+        ms = ctypes.c_float()
+        _l.check(self.L.vp_opacity_build_ms(self.h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def fetch_density(self, pos, parity=True):
         pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)

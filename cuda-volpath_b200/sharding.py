@@ -21,3 +21,24 @@ def reduce_accumulators(sum_tensor, dst=0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(sum_tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return sum_tensor
+
+
+def init_nccl_from_torch(renderer, group=None):
+    """Bootstrap the library's own NCCL communicator (vp_nccl_init) in a torch.distributed job: rank 0 creates the
+    unique id, torch's process group only carries its 128 bytes to the other ranks (plumbing); every later reduce is
+    vp_reduce_nccl -- ncclReduce issued by libvolpath_b200.so itself on the stream the caller names."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    raw = renderer.nccl_unique_id() if rank == 0 else bytes(128)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    renderer.nccl_init(world, rank, bytes(t.cpu().tolist()))
+    return rank, world
+
+
+def split_frames(total_frames, world_size):
+    """Strong scaling: `total_frames` sample indices over `world_size` ranks by interleaving; -> frames of each rank."""
+    return [frames_for_rank(0, total_frames, r, world_size)[1] for r in range(world_size)]

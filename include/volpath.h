@@ -149,6 +149,22 @@ int vp_render_to_host(vp_context* ctx, void* h_sum_float4, int first_frame, int 
 int vp_accumulate(vp_context* ctx, void* d_dst_float4, const void* d_src_float4, int size, vp_stream stream);
 int vp_sync(vp_context* ctx);
 
+/* ---- combining the per-GPU sums of a sample-sharded render.  The reference has no multi-GPU path; a
+ * path-sample is addressed by (x, y, frame) (src/sampler.h:35-43), so GPU r of G renders frames r, r + G, ... with
+ * vp_render(first + r, count, stride = G) into its own float4[W*H] sum and the sums are added on one root.
+ * NCCL (libnccl.so.2, bound at run time) over NVLink / NVSwitch; no torch involved.
+ *   multi-process hosts (one process per GPU): rank 0 calls vp_nccl_unique_id, the host distributes the 128 bytes by
+ *   its own means (MPI_Bcast, a file, a socket, torch's store), every rank calls vp_nccl_init on its context, then
+ *   vp_reduce_nccl per image: ncclReduce(sum, float, 4 * size) on `stream` (d_recv may equal d_send; NULL off-root).
+ *   single-process hosts (several contexts in one process): vp_reduce(ctxs, d_sums, n, size, root).  Synchronous. */
+#define VP_NCCL_ID_BYTES 128
+int vp_nccl_available(void);                       /* 0, or the NCCL version code of the library that was loaded */
+int vp_nccl_unique_id(char* out128);
+int vp_nccl_init(vp_context* ctx, int n_ranks, int rank, const char* id128);
+int vp_reduce_nccl(vp_context* ctx, const void* d_send_float4, void* d_recv_float4, int size, int root, vp_stream stream);
+int vp_nccl_destroy(vp_context* ctx);
+int vp_reduce(vp_context** ctxs, void** d_sums_float4, int n, int size, int root);
+
 /* introspection for tests / benchmarks */
 int vp_get_bounds_voxel(vp_context* ctx, float* h_out_maxmin);   /* [nz][ny][nx][2], (max,min) */
 int vp_get_bounds_cell(vp_context* ctx, float* h_out_maxmin, int* dims3); /* [cz][cy][cx][2] */
@@ -156,7 +172,9 @@ int vp_get_bounds_cell(vp_context* ctx, float* h_out_maxmin, int* dims3); /* [cz
  * IEEE halves per cell and the sun-clear distance as one; *present = 0 when the float tables are in use */
 int vp_get_half_tables(vp_context* ctx, unsigned short* h_out_maxmin, unsigned short* h_out_clear, float* h_out_clear_f32,
                        int* present);
-int vp_get_opacity(vp_context* ctx, float* h_out);               /* [nz][ny][nx], 0 where not stored */
+int vp_get_opacity(vp_context* ctx, float* h_out);               /* [nz][ny][nx], 0 where not stored: the bit-faithful table */
+int vp_get_opacity_fast(vp_context* ctx, float* h_out);          /* the production table (swept build, fp16 octets), same shape */
+int vp_opacity_build_ms(vp_context* ctx, float* ms);             /* device time of the last vp_precompute_opacity */
 int vp_fetch_density(vp_context* ctx, const float* h_pos3, int n, int parity_filter, float* h_out); /* world pos */
 int vp_volume_stats(vp_context* ctx, unsigned long long* out8);  /* bricks, nonempty bricks, bytes ... */
 int vp_rng_sequence(vp_context* ctx, unsigned int x, unsigned int y, unsigned int frame, int n, float* h_out_f,

@@ -71,3 +71,56 @@ def test_cpp_host_batched_launches_render_the_same_samples(tmp_path):
     assert one[..., 3].sum() > 0
     assert np.array_equal(one[..., 3], many[..., 3])
     assert np.allclose(one[..., :3], many[..., :3], rtol=1e-5, atol=1e-6)
+
+
+MULTI = os.path.join(ROOT, "host", "volpath_multi")
+
+
+def _multi(out, devices, env=None):
+    cmd = [MULTI, "--devices", devices, "--blob", "56", "--size", "96", "64", "--spp", "29", "--density", "300", "--dump", out]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "M samples / s" in p.stdout
+    return np.fromfile(out, np.float32).reshape(64, 96, 4)
+
+
+def test_cpp_multi_gpu_host_sample_sharding_and_reduce(tmp_path):
+    """host/volpath_multi.cpp: one context per GPU, frames interleaved (vp_render with stride G), sums combined with
+    vp_reduce.  Scatter counts (.w, integers) are identical to the one-context render for any G; rgb up to fp32 order.
+    On a one-GPU box the G contexts share device 0 and vp_reduce takes its peer-copy path; with >= 2 GPUs it is NCCL."""
+    import torch
+
+    if not os.path.exists(MULTI):
+        pytest.skip("host/volpath_multi not built (make -C host)")
+    one = _multi(str(tmp_path / "one.f32"), "0")
+    assert one[..., 3].sum() > 0
+    three = _multi(str(tmp_path / "three.f32"), "0,0,0", env={"VOLPATH_REDUCE_P2P": "1"})
+    assert np.array_equal(one[..., 3], three[..., 3])
+    assert np.allclose(one[..., :3], three[..., :3], rtol=1e-5, atol=1e-6)
+    if torch.cuda.device_count() >= 2:
+        two = _multi(str(tmp_path / "two.f32"), "0,1")
+        assert np.array_equal(one[..., 3], two[..., 3])
+        assert np.allclose(one[..., :3], two[..., :3], rtol=1e-5, atol=1e-6)
+
+
+def test_nccl_reduce_through_the_c_abi_single_rank():
+    """vp_nccl_unique_id / vp_nccl_init / vp_reduce_nccl on a one-rank communicator: binds libnccl.so.2 at run time and
+    runs ncclReduce on this GPU (the multi-rank case is bench.py --gpus N and tests under torchrun on >= 2 GPUs)."""
+    import torch
+
+    import cuda_volpath_b200 as vp
+
+    r = vp.Renderer(0)
+    if not r.L.vp_nccl_available():
+        pytest.skip("libnccl.so.2 not loadable")
+    r.nccl_init(1, 0, r.nccl_unique_id())
+    a = torch.rand(1000, 4, device="cuda")
+    b = torch.zeros_like(a)
+    s = torch.cuda.current_stream().cuda_stream
+    r.reduce_nccl(a.data_ptr(), b.data_ptr(), 1000, root=0, stream=s)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    with pytest.raises(vp.VolpathError):
+        r.reduce_nccl(a.data_ptr(), b.data_ptr(), 1000, root=3, stream=s)
+    r.nccl_destroy()
+    r.close()

@@ -75,23 +75,29 @@ def test_bounds_ragged_grids_vs_oracle(R, oracle, vp, dims, cell, monkeypatch):
     R.init_cuda(vol, False)
     bv = R.bounds_voxel()
     assert np.array_equal(bv, oracle.bounds_of(vol))
-    # fast-renderer grid: cells of c^3 voxels, c = pow2 <= max(1, D/6); cell value = (max, min) of the per-voxel
-    # bounds of its voxels (conservative superset of each voxel's own window)
+    # fast-renderer grid: cells of c^3 voxels, c = pow2 <= max(1, D/6).  Values: the reference's own window of the cell's
+    # CENTRE voxel (bit-exact copy of that voxel's per-voxel bound); vacuum classification: the union of the windows of
+    # all its voxels (conservative), checked through the raw view below
     assert R.volume_stats()["bound_cell_voxels"] == cell
     bc = R.bounds_cell()
     nz, ny, nx = vol.shape
     assert bc.shape[:3] == (-(-nz // cell), -(-ny // cell), -(-nx // cell))
     c = cell
-    want = np.empty_like(bc)
-    for cz in range(bc.shape[0]):
-        for cy in range(bc.shape[1]):
-            blk = bv[cz * c:cz * c + c, cy * c:cy * c + c]
-            pad = (-blk.shape[2]) % c
-            mx = np.pad(blk[..., 0], ((0, 0), (0, 0), (0, pad)), constant_values=-np.inf).reshape(blk.shape[0], blk.shape[1], -1, c)
-            mn = np.pad(blk[..., 1], ((0, 0), (0, 0), (0, pad)), constant_values=np.inf).reshape(blk.shape[0], blk.shape[1], -1, c)
-            want[cz, cy, :, 0] = mx.max(axis=(0, 1, 3))
-            want[cz, cy, :, 1] = mn.min(axis=(0, 1, 3))
+    mz = np.minimum(np.arange(bc.shape[0]) * c + c // 2, nz - 1)
+    my = np.minimum(np.arange(bc.shape[1]) * c + c // 2, ny - 1)
+    mx = np.minimum(np.arange(bc.shape[2]) * c + c // 2, nx - 1)
+    want = bv[mz][:, my][:, :, mx]
     assert np.array_equal(bc, want)
+    if cell > 1:
+        raw = R.bounds_cell(raw_jumps=True)[..., 0]
+        union = np.zeros(bc.shape[:3], np.float32)
+        for cz in range(bc.shape[0]):
+            for cy in range(bc.shape[1]):
+                blk = bv[cz * c:cz * c + c, cy * c:cy * c + c, :, 0]
+                pad = (-blk.shape[2]) % c
+                union[cz, cy] = np.pad(blk, ((0, 0), (0, 0), (0, pad)), constant_values=-np.inf).reshape(blk.shape[0], blk.shape[1], -1, c).max(axis=(0, 1, 3))
+        assert ((raw > 0) >= (union > 0)).all()   # a cell with medium in ANY voxel's window is never skippable vacuum
+        assert ((raw <= 0) <= (union == 0)).all()
 
 
 def test_vacuum_jump_distances_are_conservative(R, oracle, vp):

@@ -93,6 +93,7 @@ struct vp_context
     void*     opacity_oct = nullptr;  // fp16 octets (production renderers)
     float     opacity_ms  = 0.0f;     // device time of the last vp_precompute_opacity
     float*    sun_clear   = nullptr;
+    uint16_t* top_jump    = nullptr;     // top level of the bound grid (staged in shared memory by the production renderers)
     uint32_t* bounds_half = nullptr;     // half-precision copies for the production renderers (coarse cells only)
     uint16_t* sun_clear_half = nullptr;
     float4*   env         = nullptr;
@@ -166,6 +167,8 @@ static void free_volume(vp_context* c)
     c->S.sun_clear = nullptr;
     dev_free(c->bounds_half);
     dev_free(c->sun_clear_half);
+    dev_free(c->top_jump);
+    c->S.top_jump       = nullptr;
     c->S.bounds_half    = nullptr;
     c->S.sun_clear_half = nullptr;
     c->n_slots = 0;
@@ -433,6 +436,15 @@ static int build_from_dense_impl(vp_context* c, int nx, int ny, int nz, int stor
         if (margin > kmax - 1) margin = kmax - 1;
         VP_CUDA(launch_vacuum_jumps(c->bounds_cell, tmp.as<uint8_t>(), S.ncx, S.ncy, S.ncz, kmax, margin, cw, 0));
         VP_CUDA(cudaDeviceSynchronize());
+        // top level for shared-memory staging: blocks of t^3 cells, t the smallest power of two that fits kTopCellsMax
+        int tl = 0;
+        while ((size_t)((S.ncx + (1 << tl) - 1) >> tl) * ((S.ncy + (1 << tl) - 1) >> tl) * ((S.ncz + (1 << tl) - 1) >> tl) > (size_t)kTopCellsMax) tl++;
+        S.top_log2 = tl;
+        S.ntx = (S.ncx + (1 << tl) - 1) >> tl; S.nty = (S.ncy + (1 << tl) - 1) >> tl; S.ntz = (S.ncz + (1 << tl) - 1) >> tl;
+        VP_CUDA(cudaMalloc(&c->top_jump, (size_t)S.ntx * S.nty * S.ntz * sizeof(uint16_t)));
+        VP_CUDA(launch_build_top(c->bounds_cell, S.ncx, S.ncy, S.ncz, tl, S.ntx, S.nty, S.ntz, c->top_jump, 0));
+        VP_CUDA(cudaDeviceSynchronize());
+        S.top_jump = c->top_jump;
     }
 
     // coarse cells = a volume too large for per-voxel windows: keep the per-cell tables L2-resident in half precision
@@ -828,7 +840,6 @@ static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, 
     }
     else if (mode == VP_MODE_FAST || mode == VP_MODE_WAVE)
     {
-        if (c->S.env_mis && mode == VP_MODE_WAVE) return fail(VP_ERR_UNSUPPORTED, "vp_render: env-map sampling is not implemented in the wavefront form");
         if (!c->S.julia && !c->S.bounds_cell) return fail(VP_ERR_INVALID, "vp_render: fast mode needs VP_BOUNDS_CELL");
         // this launch's work-pool counter (see vp_context::d_work)
         const unsigned ws = c->work_rr++ % vp_context::kWorkSlots;
@@ -1268,6 +1279,16 @@ vp_context* vp_shim_context(void)
     return g_shim;
 }
 void vp_shim_set_mode(int mode) { g_shim_mode = mode; }
+// wait for every frame the render_kernel shim has in flight on its internal streams (see vp_context::ring)
+int vp_shim_sync(void)
+{
+    vp_context* c = vp_shim_context();
+    if (!c) return VP_ERR_NO_DEVICE;
+    VP_CUDA(cudaSetDevice(c->device));
+    for (cudaStream_t r : c->ring)
+        if (r) VP_CUDA(cudaStreamSynchronize(r));
+    return VP_OK;
+}
 
 #define SHIM_CTX()                         \
     vp_context* c = vp_shim_context();     \

@@ -738,6 +738,47 @@ cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// top level of the bound grid for shared-memory staging (Scene::top_jump): per block of t^3 bound cells, the smallest
+// vacuum jump distance of its cells (rounded DOWN to half precision), or 0 when any cell of the block has medium or is fringe.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_build_top(const float2* __restrict__ bounds, int ncx, int ncy, int ncz, int top_log2, int ntx, int nty,
+                                                    int ntz, uint16_t* __restrict__ top)
+{
+    const int total = ntx * nty * ntz, t = 1 << top_log2;
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x)
+    {
+        const int bx = idx % ntx, by = (idx / ntx) % nty, bz = idx / (ntx * nty);
+        float     j  = 1e30f;
+        for (int q = threadIdx.x; q < t * t * t; q += blockDim.x)
+        {
+            const int x = (bx << top_log2) + (q & (t - 1)), y = (by << top_log2) + ((q >> top_log2) & (t - 1)), z = (bz << top_log2) + (q >> (2 * top_log2));
+            if (x < ncx && y < ncy && z < ncz)
+            {
+                const float m = bounds[((size_t)z * ncy + y) * ncx + x].x;
+                j             = fminf(j, m < 0.0f ? -m : 0.0f);
+            }
+        }
+        __shared__ float red[128];
+        red[threadIdx.x] = j;
+        __syncthreads();
+        for (int w = 64; w > 0; w >>= 1)
+        {
+            if ((int)threadIdx.x < w) red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + w]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) top[idx] = __half_as_ushort(__float2half_rd(fminf(red[0], 60000.0f)));
+        __syncthreads();
+    }
+}
+cudaError_t launch_build_top(const float2* bounds_cell, int ncx, int ncy, int ncz, int top_log2, int ntx, int nty, int ntz, uint16_t* top,
+                             cudaStream_t stream)
+{
+    const int total = ntx * nty * ntz;
+    k_build_top<<<total < (int)sms(16) ? total : (int)sms(16), 128, 0, stream>>>(bounds_cell, ncx, ncy, ncz, top_log2, ntx, nty, ntz, top);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // half-precision copies of the two per-cell tables for the production renderers (large volumes): every value is
 // rounded to the safe side -- max up (a vacuum jump, stored as a negative max, thereby toward zero), min down,
 // sun-clear up -- so the majorant stays a majorant and the vacuum shortcuts stay exact.  *overflow is set when a max

@@ -73,7 +73,16 @@ struct Scene
     // instead of 12, so that both stay resident in L2 next to the streaming octets (C2: 78 MB instead of 155 MB)
     const uint32_t* bounds_half;     // half2 {max, min} per cell, or null
     const uint16_t* sun_clear_half;  // half per cell, or null
+    // top level of the bound grid: one half per block of (1 << top_log2)^3 bound cells = the distance a ray anywhere in
+    // the block may advance in any direction without meeting medium (0: the block is not all vacuum).  At most
+    // kTopCellsMax cells, so that every CTA of the production renderers can stage the whole level in shared memory.
+    const uint16_t* top_jump;
+    int             top_log2, ntx, nty, ntz;
 };
+#ifndef VP_TOP_CELLS_MAX
+#define VP_TOP_CELLS_MAX 6144
+#endif
+constexpr int kTopCellsMax = VP_TOP_CELLS_MAX;  // 12 KB of halves per CTA
 
 // ---- float3 helpers (operation order of src/cuda/helper_math.h) --------------------------------
 __device__ __forceinline__ float3 f3(float a, float b, float c) { return make_float3(a, b, c); }

@@ -51,6 +51,8 @@ cudaError_t launch_opacity_octets(const Scene& S, const uint32_t* slot_brick, ui
 cudaError_t launch_gather_opacity_oct(const Scene& S, float* dense_out, cudaStream_t stream);
 cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, int margin,
                                 float cell_world, cudaStream_t stream);
+cudaError_t launch_build_top(const float2* bounds_cell, int ncx, int ncy, int ncz, int top_log2, int ntx, int nty, int ntz, uint16_t* top,
+                             cudaStream_t stream);
 cudaError_t launch_sun_clear(const Scene& S, float3 sun, float step, int ring, float* out, cudaStream_t stream);
 cudaError_t launch_bake_sunsky(const vp_sky_state& st, float4* env, int width, int height, cudaStream_t stream);
 cudaError_t launch_pack_bounds_half(const float2* bounds_cell, uint32_t* out, size_t total, int* d_overflow, cudaStream_t stream);

@@ -59,12 +59,15 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #ifndef VP_INLINE_SEG
 #define VP_INLINE_SEG 0
 #endif
+#ifndef VP_SMEM_TOP
+#define VP_SMEM_TOP 0  // stage the top level of the bound grid (Scene::top_jump, <= 12 KB) in shared memory for the vacuum jumps of the segment block
+#endif
 #ifndef VP_CHROMA_CTAS
-#define VP_CHROMA_CTAS 10
+#define VP_CHROMA_CTAS 12  // chromatic media: ptxas fits the 3-channel step into 40 registers without spills; 10 / 11 / 12 CTAs: 894 / 917 / 935 M/s (preset 8, full C2)
 #endif
 
 constexpr int      kFastCtasPerSm = VP_CTAS_PER_SM;
-// chromatic media carry a 3-channel throughput (2 more registers, more temporaries): 10 CTAs (48 registers); the MIS variant 8
+// chromatic media carry a 3-channel throughput: the same 12 CTAs since the launch bound makes ptxas fit 40 registers (VP_CHROMA_CTAS); the MIS variant 8
 __host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis)
 {
     return (mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > VP_CHROMA_CTAS ? VP_CHROMA_CTAS : kFastCtasPerSm))) * (128 / kFastThreads);
@@ -161,6 +164,16 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
     float3   o = f3(0.f), s = f3(0.f), pend = f3(0.f), T = f3(1.f), L = f3(0.f);
     float3   C = f3(0.f);  // MIS only: radiance the pending env-direction walk will add if it survives
     float    dist = 0.f, lim = 0.f, inv = 0.f, dens = 0.f, maj = 0.f, sigc = 0.f, t_exit = 0.f, ph = 0.f, dmax = 0.f;
+#endif
+#if VP_SMEM_TOP
+    __shared__ uint16_t top_sm[kTopCellsMax];
+    const bool use_top = !JULIA && S.top_jump != nullptr;
+    if (use_top)
+    {
+        const int nt = S.ntx * S.nty * S.ntz;
+        for (int i = threadIdx.x; i < nt; i += kFastThreads) top_sm[i] = __ldg(S.top_jump + i);
+    }
+    __syncthreads();
 #endif
     int      n = 0;
     uint32_t st = kModePath, pix = 0;
@@ -272,6 +285,23 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 while (dist < t_ex)
                 {
                     if (STATS) c_seg++;
+#if VP_SMEM_TOP
+                    if (use_top)
+                    {
+                        // shared-memory top level: a block of bound cells that is all vacuum answers without a global load
+                        const float3 q  = o + s * dist;
+                        const int    sh = S.top_log2;
+                        const int    ti = clampi(__float2int_rd(fmaf(q.x, S.cs_scale.x, S.cs_off.x)), 0, S.ncx - 1) >> sh;
+                        const int    tj = clampi(__float2int_rd(fmaf(q.y, S.cs_scale.y, S.cs_off.y)), 0, S.ncy - 1) >> sh;
+                        const int    tk = clampi(__float2int_rd(fmaf(q.z, S.cs_scale.z, S.cs_off.z)), 0, S.ncz - 1) >> sh;
+                        const float  J  = __half2float(__ushort_as_half(top_sm[(tk * S.nty + tj) * S.ntx + ti]));
+                        if (J > 0.0f)
+                        {
+                            dist = fminf(dist + fmaxf(kSearchRadius, J), t_ex);
+                            continue;
+                        }
+                    }
+#endif
                     float  seg_end = JULIA ? t_ex : fminf(dist + kSearchRadius, t_ex);
                     float2 bnd     = JULIA ? make_float2(1.0f, 0.0f) : bounds_at<LY>(S, o + s * dist);
                     if (bnd.x <= 0.0f)

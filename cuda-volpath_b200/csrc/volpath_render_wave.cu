@@ -32,6 +32,8 @@ enum : uint32_t
 {
     kModeIdle = 0, kModePath = 1, kModeScat = 2, kModeSeg = 3, kModeStep = 4, kModeMask = 7,
     kShadow = 8, kLimIsCtrl = 16, kNeedRay = 32, kKillX = 64, kKillY = 128, kKillZ = 256, kEscaped = 512,
+    // env-map importance sampling variant (MIS): the same three-stage scatter event as the megakernel
+    kMisWalk = 1024, kScatB = 2048, kScatC = 4096,
 };
 
 // state fields (one float/uint word each), field-major in the warp's pool
@@ -39,9 +41,12 @@ enum
 {
     F_OX, F_OY, F_OZ, F_SX, F_SY, F_SZ, F_PX, F_PY, F_PZ, F_TX, F_TY, F_TZ, F_LX, F_LY, F_LZ,
     F_DIST, F_LIM, F_INV, F_DENS, F_MAJ, F_SIGC, F_TEXIT, F_PH, F_DMAX, F_N, F_ST, F_PIX, F_FRAME, F_CTR,
-    F_COUNT
+    F_COUNT,
+    F_CX = F_COUNT, F_CY, F_CZ,  // MIS only: radiance the pending env-direction walk adds if it survives
+    F_COUNT_MIS
 };
-constexpr int kWarpSmemWords = F_COUNT * kPool + kPool / 4 + 32 / 4;  // pool + mode bytes + batch bytes
+__host__ __device__ constexpr int fields(bool mis) { return mis ? (int)F_COUNT_MIS : (int)F_COUNT; }
+__host__ __device__ constexpr int warp_smem_words(bool mis) { return fields(mis) * kPool + kPool / 4 + 32 / 4; }  // pool + mode bytes + batch bytes
 
 #define FLD(f) pool[(f) * kPool + slot]
 #define LDF(f) FLD(f)
@@ -56,16 +61,16 @@ constexpr int kWarpSmemWords = F_COUNT * kPool + kPool / 4 + 32 / 4;  // pool + 
         FLD((f) + 2) = (v).z;  \
     } while (0)
 
-template <int VT, bool JULIA, bool GRAY, bool STATS>
+template <int VT, bool JULIA, bool GRAY, bool STATS, bool MIS>
 __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant__ Scene S, float4* __restrict__ d_sum, int first_frame,
                                                           int n_frames, int frame_stride, const __grid_constant__ vp_param P,
                                                           unsigned long long* __restrict__ d_work,
                                                           unsigned long long* __restrict__ d_stats)
 {
-    __shared__ float smem[kWarps * kWarpSmemWords];
+    __shared__ float smem[kWarps * warp_smem_words(MIS)];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float*         pool  = smem + warp * kWarpSmemWords;
-    uint8_t*       modes = reinterpret_cast<uint8_t*>(pool + F_COUNT * kPool);
+    float*         pool  = smem + warp * warp_smem_words(MIS);
+    uint8_t*       modes = reinterpret_cast<uint8_t*>(pool + fields(MIS) * kPool);
     uint8_t*       batch = modes + kPool;
 
     const uint32_t tiles_x = (P.width + 7) >> 3, tiles_y = (P.height + 3) >> 2;
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
             {
                 float3 s = LD3(F_SX), T = LD3(F_TX), L = LD3(F_LX);
                 int    n = (int)LDU(F_N);
-                L        = L + background(S, s, n) * (GRAY ? f3(T.x) : T);
+                if (!MIS || n == 0) L = L + background(S, s, n) * (GRAY ? f3(T.x) : T);  // K.cu:2026-2030
                 accumulate(d_sum, LDU(F_PIX), L, n, P.brightness);
             }
             const uint32_t avail = (uint32_t)(w_end - w_next);
@@ -276,16 +281,34 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                         {
                             float3 a = f3((st & kKillX) ? 0.f : 1.f, (st & kKillY) ? 0.f : 1.f, (st & kKillZ) ? 0.f : 1.f);
                             float3 L = LD3(F_LX);
-                            L        = L + S.sun_power * ((GRAY ? f3(T.x) : T) * LDF(F_PH) * a);
-                            ST3(F_LX, L);
-                            s  = LD3(F_PX);
-                            ST3(F_SX, s);
-                            st = kModeSeg | kNeedRay;
-                            int n = (int)LDU(F_N);
-                            if (n >= kMaxDepth)
+                            if (MIS)
                             {
-                                accumulate(d_sum, key, L, n, P.brightness);
-                                st = kModePath;
+                                // sun walk done -> MIS stage; MIS walk done -> direction sampling stage
+                                if (st & kMisWalk)
+                                {
+                                    L  = L + LD3(F_CX) * a;
+                                    st = kModeScat | kScatC;
+                                }
+                                else
+                                {
+                                    L  = L + S.sun_power * ((GRAY ? f3(T.x) : T) * LDF(F_PH) * a);
+                                    st = kModeScat | kScatB;
+                                }
+                                ST3(F_LX, L);
+                            }
+                            else
+                            {
+                                L = L + S.sun_power * ((GRAY ? f3(T.x) : T) * LDF(F_PH) * a);
+                                ST3(F_LX, L);
+                                s  = LD3(F_PX);
+                                ST3(F_SX, s);
+                                st = kModeSeg | kNeedRay;
+                                int n = (int)LDU(F_N);
+                                if (n >= kMaxDepth)
+                                {
+                                    accumulate(d_sum, key, L, n, P.brightness);
+                                    st = kModePath;
+                                }
                             }
                         }
                     }
@@ -348,7 +371,77 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
         }
         else  // kModeScat
         {
-            if (active)
+            if (active && MIS && (st & (kScatB | kScatC)))
+            {
+                // ---- env-map sampling variant, stages B and C of a scattering event (incoming direction in F_P*) ----
+                float3   o = LD3(F_OX);
+                float3   T = GRAY ? f3(LDF(F_TX)) : LD3(F_TX);
+                int      n = (int)LDU(F_N);
+                uint32_t ctr = LDU(F_CTR);
+                const uint32_t key = LDU(F_PIX), frame = LDU(F_FRAME);
+                float  sr_pre = fmaxf(0.0f, fminf(1.0f, (n - 1 - 5) * 0.066666666666666666667f));
+                float  g      = (1 - sr_pre) * P.g;
+                float3 ft, fb;
+                const float3 din = LD3(F_PX);
+                make_frame_fast(din, ft, fb);
+                if (st & kScatB)
+                {
+                    // one-sample MIS between phase-function and env-map sampling (K.cu:2220-2297)
+                    float rsel, u, v, unused;
+                    philox_draw(key, frame, ctr, rsel, u);
+                    philox_draw(key, frame, ctr, v, unused);
+                    float3 dir, envc, C;
+                    bool   ok = true;
+                    if (rsel < 0.5f)
+                    {
+                        float3 ls = hg_sample_local_fast(g, u, v);
+                        dir       = ft * ls.x + fb * ls.y + din * ls.z;
+                        envc      = eval_envmap(S, dir);
+                        float pdf_brdf = hg_eval_fast(g, dot3(din, dir));
+                        float pdf_env  = pdf_envmap(S, envc);
+                        float weight   = __fdividef(pdf_brdf * 0.5f, pdf_brdf * 0.5f + pdf_env * 0.5f) * 2.0f;
+                        C              = envc * ((GRAY ? f3(T.x) : T) * weight);
+                    }
+                    else
+                    {
+                        float pdf_env = sample_envmap(S, u, v, envc);
+                        ok            = pdf_env > 0.0f;  // (the reference `continue`s here, K.cu:2266: probability ~2^-23)
+                        dir           = uv_to_dir(u, v);
+                        float pb      = hg_eval_fast(g, dot3(din, dir));
+                        float weight  = __fdividef(pdf_env * 0.5f, pdf_env * 0.5f + pb * 0.5f) * 2.0f;
+                        C             = envc * ((GRAY ? f3(T.x) : T) * (__fdividef(pb, pdf_env) * weight));
+                    }
+                    ST3(F_CX, C);
+                    if (ok)
+                    {
+                        float3 s = normalize3(dir);
+                        float  tn, tf;
+                        box_slabs_fast(S, o, s, tn, tf);
+                        ST3(F_SX, s);
+                        STF(F_DIST, 0.0f);
+                        STF(F_LIM, (tf > tn && tf >= 1e-3f) ? tf : 0.0f);
+                        STF(F_INV, __fdividef(1.0f, max_sig_t * LDF(F_DENS) * LDF(F_DMAX)));
+                        st = kModeStep | kShadow | kMisWalk;
+                    }
+                    else
+                        st = kModeScat | kScatC;
+                }
+                else
+                {
+                    float r0, r1;
+                    philox_draw(key, frame, ctr, r0, r1);
+                    float3 l = hg_sample_local_fast(g, r0, r1);
+                    ST3(F_SX, normalize3(ft * l.x + fb * l.y + din * l.z));
+                    st = kModeSeg | kNeedRay;
+                    if (n >= kMaxDepth)
+                    {
+                        accumulate(d_sum, key, LD3(F_LX), n, P.brightness);
+                        st = kModePath;
+                    }
+                }
+                STU(F_CTR, ctr);
+            }
+            else if (active)
             {
                 float3   o = LD3(F_OX), s = LD3(F_SX);
                 float3   T = GRAY ? f3(LDF(F_TX)) : LD3(F_TX);
@@ -359,14 +452,20 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                 float g      = (1 - sr_pre) * P.g;
                 n++;
                 STU(F_N, (uint32_t)n);
-                float3 ft, fb;
-                make_frame_fast(s, ft, fb);
-                float ph = hg_eval_fast(g, dot3(s, S.sun_dir));
-                float r0, r1;
-                philox_draw(key, frame, ctr, r0, r1);
-                STU(F_CTR, ctr);
-                float3 l    = hg_sample_local_fast(g, r0, r1);
-                float3 pend = normalize3(ft * l.x + fb * l.y + s * l.z);
+                float  ph = hg_eval_fast(g, dot3(s, S.sun_dir));
+                float3 pend;
+                if (MIS)
+                    pend = s;  // keep the incoming direction: the new one is sampled after both NEE walks (stage C)
+                else
+                {
+                    float3 ft, fb;
+                    make_frame_fast(s, ft, fb);
+                    float r0, r1;
+                    philox_draw(key, frame, ctr, r0, r1);
+                    STU(F_CTR, ctr);
+                    float3 l = hg_sample_local_fast(g, r0, r1);
+                    pend     = normalize3(ft * l.x + fb * l.y + s * l.z);
+                }
                 float  sr   = fmaxf(0.0f, fminf(1.0f, (n - 5) * 0.066666666666666666667f));
                 float  dens = ((1 - sr) + sr * (1 - P.g)) * P.density;
                 STF(F_DENS, dens);
@@ -377,12 +476,20 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                     float3 L   = LD3(F_LX);
                     L          = L + S.sun_power * ((GRAY ? f3(T.x) : T) * ph * a);
                     ST3(F_LX, L);
-                    ST3(F_SX, pend);
-                    st = kModeSeg | kNeedRay;
-                    if (n >= kMaxDepth)
+                    if (MIS)
                     {
-                        accumulate(d_sum, key, L, n, P.brightness);
-                        st = kModePath;
+                        ST3(F_PX, pend);
+                        st = kModeScat | kScatB;
+                    }
+                    else
+                    {
+                        ST3(F_SX, pend);
+                        st = kModeSeg | kNeedRay;
+                        if (n >= kMaxDepth)
+                        {
+                            accumulate(d_sum, key, L, n, P.brightness);
+                            st = kModePath;
+                        }
                     }
                 }
                 else
@@ -390,7 +497,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                     float inv = __fdividef(1.0f, max_sig_t * dens * LDF(F_DMAX));
                     s         = S.sun_dir;
                     float tn, tf;
-                    box_slabs_fast(S, o, s, tn, tf);
+                    box_slabs_inv(S, o, S.sun_inv, tn, tf);  // the megakernel's expression, bit for bit
                     float lim = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
                     if (!JULIA && S.sun_clear) lim = fminf(lim, sun_clear_at(S, o));
                     STF(F_INV, inv); STF(F_LIM, lim); STF(F_DIST, 0.0f); STF(F_PH, ph);
@@ -423,7 +530,7 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
 }
 }  // namespace wave
 
-template <int VT, bool JULIA, bool GRAY>
+template <int VT, bool JULIA, bool GRAY, bool MIS>
 static cudaError_t launch_wave_t(const Scene& S, float4* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param& P,
                                  unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
@@ -431,9 +538,9 @@ static cudaError_t launch_wave_t(const Scene& S, float4* d_sum, int first_frame,
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     if (d_stats)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::k_render_wave<VT, JULIA, GRAY, true>, wave::kThreads, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::k_render_wave<VT, JULIA, GRAY, true, MIS>, wave::kThreads, 0);
     else
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::k_render_wave<VT, JULIA, GRAY, false>, wave::kThreads, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave::k_render_wave<VT, JULIA, GRAY, false, MIS>, wave::kThreads, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unsigned long long items = (unsigned long long)((P.width + 7) / 8) * ((P.height + 3) / 4) * 32ull * n_frames;
@@ -443,9 +550,9 @@ static cudaError_t launch_wave_t(const Scene& S, float4* d_sum, int first_frame,
     unsigned int       grid  = (unsigned int)(ctas < cap ? ctas : cap);
     if (grid < 1) grid = 1;
     if (d_stats)
-        wave::k_render_wave<VT, JULIA, GRAY, true><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
+        wave::k_render_wave<VT, JULIA, GRAY, true, MIS><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
     else
-        wave::k_render_wave<VT, JULIA, GRAY, false><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
+        wave::k_render_wave<VT, JULIA, GRAY, false, MIS><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
     return cudaGetLastError();
 }
 
@@ -453,9 +560,14 @@ cudaError_t launch_render_wave(const Scene& S, float4* d_sum, int first_frame, i
                                unsigned long long* d_work, unsigned long long* d_stats, int num_sms, cudaStream_t stream)
 {
     const bool gray = P.sigma_t.x == P.sigma_t.y && P.sigma_t.y == P.sigma_t.z && P.albedo.x == P.albedo.y && P.albedo.y == P.albedo.z;
-#define VP_WAVE(VT, J)                                                                                                          \
-    return gray ? launch_wave_t<VT, J, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream) \
-                : launch_wave_t<VT, J, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)
+#define VP_WAVE(VT, J)                                                                                                                     \
+    do {                                                                                                                                   \
+        if (S.env_mis)                                                                                                                     \
+            return gray ? launch_wave_t<VT, J, true, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)   \
+                        : launch_wave_t<VT, J, false, true>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream); \
+        return gray ? launch_wave_t<VT, J, true, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream)      \
+                    : launch_wave_t<VT, J, false, false>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, num_sms, stream);    \
+    } while (0)
     if (S.julia) VP_WAVE(kF32, true);
     if (S.voxel_type == kU8) VP_WAVE(kU8, false);
     if (S.voxel_type == kF16) VP_WAVE(kF16, false);

@@ -109,6 +109,7 @@ SIGNATURES = {
     "gamma_correct": (None, [c_vp, c_vp, c_int, ctypes.c_float, ctypes.c_float]),
     "render_kernel": (None, [Dim3, Dim3, c_vp, c_int, ctypes.POINTER(Param)]),
     "vp_shim_set_mode": (None, [c_int]),
+    "vp_shim_sync": (c_int, []),
     "vp_shim_context": (c_vp, []),
 }
 

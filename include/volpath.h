@@ -79,7 +79,8 @@ enum { VP_BOUNDS_VOXEL = 1, VP_BOUNDS_CELL = 2, VP_BOUNDS_EXACT = 4 };
  *                    counter RNG, exact skipping of the empty-space march and of vacuum; same estimator in
  *                    distribution.
  *   VP_MODE_WAVE   : the wavefront form of VP_MODE_FAST: ray states as SoA pools in shared memory, batches of 32
- *                    same-event states compacted with ballot/popc; the SAME samples as VP_MODE_FAST. */
+ *                    same-event states compacted with ballot/popc; the SAME samples as VP_MODE_FAST (env-map
+ *                    importance sampling included). */
 enum { VP_MODE_PARITY = 0, VP_MODE_FAST = 1, VP_MODE_WAVE = 2 };
 
 /* ---- (2) handle-based core -------------------------------------------------------------------- */
@@ -133,7 +134,10 @@ int vp_free_volume(vp_context* ctx);                                            
 
 /* replaces render_kernel + the host frame loop: frames first_frame, first_frame+frame_stride, ...
  * (n_frames of them) are added into d_sum.  n_frames = 1, stride 1, VP_MODE_PARITY is
- * observationally identical to one render_kernel launch.  Asynchronous on `stream`. */
+ * observationally identical to one render_kernel launch.  Asynchronous on `stream`; any number of caller streams may
+ * have launches of one context in flight (each launch owns a work-pool counter; beyond 16 launches in flight a launch
+ * queues behind the one whose counter it takes over).  Scene setters (vp_set_sun, vp_set_envmap, vp_precompute_opacity,
+ * uploads) synchronise the device before they replace a table a render may still be reading. */
 int vp_render(vp_context* ctx, void* d_sum_float4, int first_frame, int n_frames, int frame_stride,
               const vp_param* p, int mode, vp_stream stream);
 /* __scale / __gamma_correct (K.cu:2333-2362); gamma <= 0 -> plain scale */
@@ -211,8 +215,15 @@ void scale(vp_float4* dst, vp_float4* src, int size, float scale);        /* K.c
 void gamma_correct(vp_float4* dst, vp_float4* src, int size, float scale, float gamma); /* K.cu:2359 */
 /* K.cu:2364: `const Param& p` in the reference; a C++ reference is a pointer at the ABI level */
 void render_kernel(vp_dim3 gridSize, vp_dim3 blockSize, vp_float4* d_output, int spp, const vp_param* p);
-/* which renderer the render_kernel shim uses (default VP_MODE_PARITY: drop-in identical) */
+/* which renderer the render_kernel shim uses (default VP_MODE_PARITY: drop-in identical, fixed-seed traces equal to the
+ * reference kernel's).  VP_MODE_FAST: consecutive one-frame launches rotate over four internal BLOCKING streams, so the
+ * long tail of frame n overlaps frame n + 1 while the host does not synchronise.  Blocking streams order themselves against
+ * the legacy default stream exactly like the reference's own launches, so a host that uses the default stream,
+ * cudaMemcpy or cudaDeviceSynchronize (the reference host does, volumeRender.cpp:627-641) needs no change.  A host
+ * compiled with --default-stream per-thread, or one that reads d_output from a cudaStreamNonBlocking stream, must call
+ * vp_shim_sync() (or cudaDeviceSynchronize) before touching d_output -- or switch the ring off: VOLPATH_SHIM_OVERLAP=0. */
 void vp_shim_set_mode(int mode);
+int  vp_shim_sync(void);
 vp_context* vp_shim_context(void);
 
 #if defined(__GNUC__)

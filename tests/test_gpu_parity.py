@@ -563,8 +563,14 @@ def test_env_sampling_parity_vs_reference_cuda_kernel(R, oracle, vp):
         for sl in (np.s_[..., :3], np.s_[..., 3]):
             ma, mb, mf = a[sl].mean(), b[sl].mean(), f[sl].mean()
             assert abs(mf - 0.5 * (ma + mb)) <= 3 * abs(ma - mb) + 0.004 * ma, (ma, mb, mf)
-        with pytest.raises(vp.VolpathError, match="wavefront"):
-            R.render(P, 0, 1, mode=vp.MODE_WAVE)
+        # the wavefront form carries the same three-stage scatter event: the SAME samples as the megakernel
+        w = R.render(P, 0, 64, mode=vp.MODE_WAVE)
+        f64 = R.render(P, 0, 64, mode=vp.MODE_FAST)
+        # (393 k paths: the two kernels are separate compilations of the same expressions, so once in ~10^5 paths a
+        # differently contracted float lands on the other side of an accept / reject threshold)
+        differ = w[..., 3] != f64[..., 3]
+        assert differ.sum() <= 4, (int(differ.sum()), w[..., 3].sum(), f64[..., 3].sum())
+        assert np.allclose(w[..., :3][~differ], f64[..., :3][~differ], rtol=2e-5, atol=1e-6)
     finally:
         R.set_env_sampling(False)
     # the two estimators (env picked up by escaping paths / sampled at every scatter event) agree in the mean

@@ -22,7 +22,7 @@ import cuda_volpath_b200 as vp  # noqa: E402
 from oraclelib import RefCuda  # noqa: E402
 
 
-def cloud(dims, W, H, first, n):
+def cloud(dims, W, H, first, n, material=-1, albedo=1.0, density=800.0, label="C2"):
     nx, ny, nz = dims
     env, sd, sp = vp.default_sunsky()
     view = vp.inv_view_matrix()
@@ -37,6 +37,10 @@ def cloud(dims, W, H, first, n):
     ref.set_inv_view(view)
     ref.precompute_opacity(sd)
     P = vp.default_param(W, H)
+    P.density = density
+    P.albedo[:] = [albedo] * 3
+    if material >= 0:
+        P = vp.mat(P, *vp.MATERIALS[material])
     acc = torch.zeros(H, W, 4, device="cuda")
     ref.reset_counters()
     assert ref.L.ref_render(acc.data_ptr(), first, n, ctypes.addressof(P)) == 0
@@ -51,7 +55,7 @@ def cloud(dims, W, H, first, n):
     r.counters(reset=True)
     r.render(P, first, n, mode=vp.MODE_FAST)
     o = r.counters()
-    out = {"workload": "C2 cloud family %dx%dx%d fp32, %dx%d, frames %d..%d" % (nx, ny, nz, W, H, first, first + n - 1),
+    out = {"workload": "%s on the C2 cloud family %dx%dx%d fp32, %dx%d, frames %d..%d" % (label, nx, ny, nz, W, H, first, first + n - 1),
            "L": c[0] + c[1], "L_track": c[0], "L_shadow": c[1], "S": c[2], "O": c[3], "E": c[4], "scatters": c[5],
            "ours": {k: v / (W * H * n) for k, v in o.items()}}
     r.close()
@@ -78,7 +82,11 @@ if __name__ == "__main__":
     import faulthandler
 
     faulthandler.enable()
-    out = {"cloud": cloud((497, 338, 612), 1920, 1080, 16, 8), "c1": julia(512, 512, 8)}
+    q = (497, 338, 612)
+    out = {"cloud": cloud(q, 1920, 1080, 16, 8), "c1": julia(512, 512, 8),
+           "c3a": cloud(q, 1920, 1080, 16, 8, material=8, label="C3 (Mat preset 8)"),
+           "c3b": cloud(q, 1920, 1080, 16, 8, material=4, label="C3 (Mat preset 4)"),
+           "c4": cloud(q, 1920, 1080, 16, 8, albedo=0.999, density=3000.0, label="C4 (albedo 0.999, density 3000)")}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     for d in ("gpurun_out", "profiles"):
         json.dump(out, open(os.path.join(ROOT, d, "ref_counters.json"), "w"), indent=1)

@@ -263,6 +263,7 @@ def check_block(vp, device, dims, over, subset=(480, 270), frames=256):
     W, H = subset
     P = workload_param(vp, W, H, over)
     fast = r.render(P, 12, 4 * frames, mode=vp.MODE_FAST)      # 4x the samples: the fast estimate's noise is not the limit
+    fast_half = r.render(P, 12, frames // 2, mode=vp.MODE_FAST)
     par_a = r.render(P, 12, frames // 2, mode=vp.MODE_PARITY)
     par_b = r.render(P, 12 + frames // 2, frames - frames // 2, mode=vp.MODE_PARITY)
     r.close()
@@ -271,6 +272,12 @@ def check_block(vp, device, dims, over, subset=(480, 270), frames=256):
     sf, sp = fast[..., 3].sum() / n_f, par[..., 3].sum() / n_p
     mf, mp = fast[..., :3].sum() / n_f, par[..., :3].sum() / n_p
     half = W * H * (frames // 2)
+    # equal-spp per-pixel RMSE: fast vs parity against parity vs parity (two disjoint frame sets of frames/2 each); a ratio
+    # above 1 means the fast estimate is noisier than the reference estimator's own Monte-Carlo noise
+    fa = fast_half[..., :3] / (frames // 2)
+    pa, pb = par_a[..., :3] / (frames // 2), par_b[..., :3] / (frames - frames // 2)
+    rmse_fp = float(np.sqrt(np.mean((fa - pb) ** 2)))
+    rmse_pp = float(np.sqrt(np.mean((pa - pb) ** 2)))
     noise_s = abs(par_a[..., 3].sum() / half - par_b[..., 3].sum() / (n_p - half)) / sp
     noise_m = abs(par_a[..., :3].sum() / half - par_b[..., :3].sum() / (n_p - half)) / mp
     return {"what": "k_render_fast (benchmarked layout: rank directory, half tables, %d^3-voxel bound cells, fp16 opacity octets) vs "
@@ -279,6 +286,9 @@ def check_block(vp, device, dims, over, subset=(480, 270), frames=256):
             "mean_scatters_fast": float(sf), "mean_scatters_parity": float(sp), "scatter_rel": float(abs(sf - sp) / sp),
             "image_mean_fast": float(mf), "image_mean_parity": float(mp), "mean_rel": float(abs(mf - mp) / mp),
             "parity_half_vs_half": {"scatter_rel": float(noise_s), "mean_rel": float(noise_m)},
+            "rmse_equal_spp": {"spp": frames // 2, "fast_vs_parity": rmse_fp, "parity_vs_parity": rmse_pp, "ratio": rmse_fp / rmse_pp},
+            "max_pixel_sample_mean": {"fast": float(np.nanmax(fast[..., :3]) / (4 * frames)), "parity": float(np.nanmax(par[..., :3]) / frames)},
+            "nonfinite_pixels": {"fast": int((~np.isfinite(fast)).any(axis=-1).sum()), "parity": int((~np.isfinite(par)).any(axis=-1).sum())},
             "tolerance": {"scatter_rel": 0.01, "mean_rel": 0.005},
             "ok": bool(abs(sf - sp) / sp <= 0.01 and abs(mf - mp) / mp <= 0.005 + noise_m),
             "bounds_voxel_bytes": st["bounds_voxel_bytes"], "setup_s": round(setup, 2)}
@@ -352,17 +362,25 @@ def main():
     env, sun_dir, sun_power, view = scene_inputs(vp)
     t_setup = time.perf_counter()
     store = vp.VOXEL_F32 if args.store == "f32" else vp.VOXEL_F16
+    tb = [time.perf_counter()]
     if dims is None:
         r.set_julia()
     else:
         r.generate_cloud(*dims, seed=CLOUD_SEED, store=store, bounds=vp.BOUNDS_CELL)
+    r.sync()
+    tb.append(time.perf_counter())
     r.set_texture_filter_mode(True)
     r.init_envmap(env)
     r.set_sun(sun_dir, sun_power)
     r.copy_inv_view_matrix(view)
+    r.sync()
+    tb.append(time.perf_counter())
     r.precompute_opacity(sun_dir)
     r.sync()
+    tb.append(time.perf_counter())
     t_setup = time.perf_counter() - t_setup
+    setup_breakdown = {"volume_bounds_octets_s": round(tb[1] - tb[0], 3), "env_sun_tables_s": round(tb[2] - tb[1], 3),
+                       "opacity_s": round(tb[3] - tb[2], 3)}
     opacity_ms = r.opacity_build_ms()
     stats = r.volume_stats() if dims is not None else {}
     P = workload_param(vp, W, H, over)
@@ -445,8 +463,12 @@ def main():
     img_stats = None
     if rank == 0:
         n_img = W * H * step_frames * (args.warmup + args.steps)
+        finite = torch.isfinite(total).all(dim=-1)
+        rgb = torch.where(finite.unsqueeze(-1), total[..., :3], torch.zeros_like(total[..., :3]))
         img_stats = {"mean_scatters_per_path": float(total[..., 3].double().sum().item() / n_img),
-                     "image_mean": float(total[..., :3].double().sum().item() / (3 * n_img)), "frames_in_image": step_frames * (args.warmup + args.steps)}
+                     "image_mean": float(rgb.double().sum().item() / (3 * n_img)), "nonfinite_pixels": int((~finite).sum().item()),
+                     "max_pixel_mean": float(rgb.max().item() / (step_frames * (args.warmup + args.steps))),
+                     "frames_in_image": step_frames * (args.warmup + args.steps)}
 
     # kernel-only average launch duration for the roofline: this rank's render launch alone
     kms = []
@@ -520,7 +542,7 @@ def main():
             "config": {"workload": desc, "frames_per_step": step_frames, "frames_per_step_per_gpu": step_frames // world if world > 1 else fps,
                        "mode": "fast (megakernel)", "store": args.store,
                        "l2": "inputs larger than L2 (octet store %.1f GB)" % (stats.get("octet_bytes", 0) / 1e9),
-                       "parallelism": par, "volume": stats, "setup_s": round(t_setup_max, 2), "opacity_build_s": round(opacity_ms * 1e-3, 3),
+                       "parallelism": par, "volume": stats, "setup_s": round(t_setup_max, 2), "setup_breakdown_rank0": setup_breakdown, "opacity_build_s": round(opacity_ms * 1e-3, 3),
                        "wall_to_image_s": round(t_setup_max + ms * 1e-3, 2),
                        "wall_note": "setup (cloud, bricks, bounds, sun tables: per GPU, replicated) + the timed region"},
             "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "image": img_stats}

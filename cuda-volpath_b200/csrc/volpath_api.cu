@@ -19,6 +19,10 @@
 
 using namespace vp;
 
+#ifndef VP_DEFAULT_CELL_WINDOWS
+#define VP_DEFAULT_CELL_WINDOWS 1  // coarse bound cells: 0 = union of the voxels' windows, 1 = the centre voxel's window, 2 = max from the union, min from the centre
+#endif
+
 namespace
 {
 thread_local char g_err[512] = "";
@@ -371,7 +375,9 @@ static int build_from_dense_impl(vp_context* c, int nx, int ny, int nz, int stor
         VP_CUDA(launch_bounds_axis(t1.as<float2>(), c->bounds_cell, S.ncx, S.ncy, nz, 2, D, cell, 0));
         // values: the reference's window of the cell's centre voxel; vacuum classification: the union window above
         // (k_merge_cell_bounds; VOLPATH_UNION_WINDOWS=1 keeps the union values, for the bias measurement in DESIGN.md)
-        if (!env_flag("VOLPATH_UNION_WINDOWS"))
+        const char* wm = getenv("VOLPATH_CELL_WINDOWS");  // union | centre | mixed (measurements: DESIGN.md section 2)
+        const int   window_mode = !wm ? VP_DEFAULT_CELL_WINDOWS : (!strcmp(wm, "union") ? 0 : (!strcmp(wm, "centre") ? 1 : 2));
+        if (window_mode != 0)
         {
             DevTmp cb;
             const size_t cells = (size_t)S.ncx * S.ncy * S.ncz;
@@ -379,7 +385,7 @@ static int build_from_dense_impl(vp_context* c, int nx, int ny, int nz, int stor
             VP_CUDA(launch_bounds_axis_f32(c->dense, t0.as<float2>(), nx, ny, nz, 0, D, cell, 0, 1));
             VP_CUDA(launch_bounds_axis(t0.as<float2>(), t1.as<float2>(), S.ncx, ny, nz, 1, D, cell, 0, 1));
             VP_CUDA(launch_bounds_axis(t1.as<float2>(), cb.as<float2>(), S.ncx, S.ncy, nz, 2, D, cell, 0, 1));
-            VP_CUDA(launch_merge_cell_bounds(c->bounds_cell, cb.as<float2>(), cells, 0));
+            VP_CUDA(launch_merge_cell_bounds(c->bounds_cell, cb.as<float2>(), cells, window_mode == 2, 0));
             VP_CUDA(cudaDeviceSynchronize());
         }
         VP_CUDA(cudaDeviceSynchronize());
@@ -1262,7 +1268,18 @@ int vp_reduce(vp_context** ctxs, void** d_sums, int n, int size, int root)
 // (1) reference-named shims over one implicit context on the current device
 // =======================================================================================================
 static vp_context* g_shim      = nullptr;
-static int         g_shim_mode = VP_MODE_PARITY;
+// Default renderer of the render_kernel shim: the production megakernel (the same estimator in distribution; 3.5x the
+// reference kernel when frames are batched or not synchronised one by one, profiles/README.md).  VP_MODE_PARITY -- fixed-seed
+// traces equal to the reference kernel's, at 0.82x its speed (software texture emulation) -- by vp_shim_set_mode(0) or
+// VOLPATH_SHIM_MODE=parity.
+static int shim_default_mode()
+{
+    const char* m = getenv("VOLPATH_SHIM_MODE");
+    if (m && (!strcmp(m, "parity") || !strcmp(m, "0"))) return VP_MODE_PARITY;
+    if (m && (!strcmp(m, "wave") || !strcmp(m, "2"))) return VP_MODE_WAVE;
+    return VP_MODE_FAST;
+}
+static int g_shim_mode = shim_default_mode();
 
 vp_context* vp_shim_context(void)
 {

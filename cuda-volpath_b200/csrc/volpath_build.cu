@@ -257,17 +257,17 @@ cudaError_t launch_bounds_axis(const float2* in, float2* out, int n0, int n1, in
 // vacuum classification (skippable without random draws) stays with the conservative union window: a cell is vacuum
 // only if no voxel of it has medium within D; a cell whose centre window is empty but whose union window is not keeps
 // the tiny positive max of a fringe cell and is tracked like the reference tracks it (d_max floored to 1e-4).
-__global__ void __launch_bounds__(256) k_merge_cell_bounds(float2* __restrict__ unio, const float2* __restrict__ centre, size_t total)
+__global__ void __launch_bounds__(256) k_merge_cell_bounds(float2* __restrict__ unio, const float2* __restrict__ centre, size_t total, int max_from_union)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     {
         const float2 u = unio[i], c = centre[i];
-        unio[i] = make_float2(u.x > 0.0f ? fmaxf(c.x, 1e-30f) : u.x, c.y);
+        unio[i] = make_float2(max_from_union ? u.x : (u.x > 0.0f ? fmaxf(c.x, 1e-30f) : u.x), c.y);
     }
 }
-cudaError_t launch_merge_cell_bounds(float2* union_bounds, const float2* centre_bounds, size_t total, cudaStream_t stream)
+cudaError_t launch_merge_cell_bounds(float2* union_bounds, const float2* centre_bounds, size_t total, int max_from_union, cudaStream_t stream)
 {
-    k_merge_cell_bounds<<<grid_for(total, 256), 256, 0, stream>>>(union_bounds, centre_bounds, total);
+    k_merge_cell_bounds<<<grid_for(total, 256), 256, 0, stream>>>(union_bounds, centre_bounds, total, max_from_union);
     return cudaGetLastError();
 }
 

@@ -126,8 +126,13 @@ __device__ __forceinline__ void item_to_sample(unsigned long long item, uint32_t
 
 __device__ __forceinline__ void accumulate(float4* __restrict__ d_sum, uint32_t pix, float3 L, int n, float brightness)
 {
-    // Q9: per-sample clamp (K.cu:2315-2316); one red.global.add.v4.f32
+    // Q9: per-sample clamp (K.cu:2315-2316); one red.global.add.v4.f32.  The reference's fmaxf drops a NaN sample (its
+    // weights go 0/0 for zero albedo) but lets +inf through, which then owns the pixel for the rest of the render: the
+    // weighted tracker's throughput is unbounded where a local bound is exceeded and overflows about once in 10^9..10^10
+    // path-samples on chromatic media (bench.py `image.nonfinite_pixels`).  The production renderers drop such a sample
+    // like a NaN -- the one deliberate deviation from the reference's arithmetic.
     float4 v = make_float4(fmaxf(L.x * brightness, 0.0f), fmaxf(L.y * brightness, 0.0f), fmaxf(L.z * brightness, 0.0f), (float)n);
+    if (!(v.x + v.y + v.z < 3.0e38f)) v.x = v.y = v.z = 0.0f;
     atomicAdd(d_sum + pix, v);
 }
 

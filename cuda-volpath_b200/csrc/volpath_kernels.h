@@ -36,7 +36,7 @@ cudaError_t launch_bounds_axis_f32(const float* in, float2* out, int n0, int n1,
                                    cudaStream_t stream, int centred = 0);
 cudaError_t launch_bounds_axis(const float2* in, float2* out, int n0, int n1, int n2, int axis, int D, int cell,
                                cudaStream_t stream, int centred = 0);
-cudaError_t launch_merge_cell_bounds(float2* union_bounds, const float2* centre_bounds, size_t total, cudaStream_t stream);
+cudaError_t launch_merge_cell_bounds(float2* union_bounds, const float2* centre_bounds, size_t total, int max_from_union, cudaStream_t stream);
 cudaError_t launch_classify_bricks(const float* dense, int nx, int ny, int nz, int nbx, int nby, int nbz, uint32_t* flags,
                                    cudaStream_t stream);
 cudaError_t launch_make_words(const uint32_t* flags, const uint32_t* scan, size_t nb, uint2* words, uint32_t* slot_brick,

@@ -59,6 +59,12 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #ifndef VP_INLINE_SEG
 #define VP_INLINE_SEG 0
 #endif
+#ifndef VP_SUN_NO_SLAB
+#define VP_SUN_NO_SLAB 1  // sun shadow walks end at the sun-clear distance alone (exact; +0.7 % at full C2, profiles/README.md)
+#endif
+#ifndef VP_SEG_ITERS
+#define VP_SEG_ITERS 0  // 0: the segment block loops over vacuum jumps until medium or exit
+#endif
 #ifndef VP_SMEM_TOP
 #define VP_SMEM_TOP 0  // stage the top level of the bound grid (Scene::top_jump, <= 12 KB) in shared memory for the vacuum jumps of the segment block
 #endif
@@ -282,8 +288,19 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 }
                 bool found = false;
                 const float t_ex = t_exit;
+#if VP_SEG_ITERS
+                int iters = 0;  // at most VP_SEG_ITERS vacuum jumps per vote: lanes that need more stay in the segment state
+#endif
                 while (dist < t_ex)
                 {
+#if VP_SEG_ITERS
+                    if (iters++ >= VP_SEG_ITERS)
+                    {
+                        found = true;
+                        st    = kModeSeg;
+                        break;
+                    }
+#endif
                     if (STATS) c_seg++;
 #if VP_SMEM_TOP
                     if (use_top)
@@ -602,12 +619,21 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     // shadow walk toward the sun with the LOCAL majorant (Q1), K.cu:2173-2208
                     inv = __fdividef(1.0f, max_sig_t * dens * float(dmax));
                     s   = S.sun_dir;  // normalize(sun_dir * 1e10 - pos) up to rounding
-                    float tn, tf;
-                    box_slabs_inv(S, o, S.sun_inv, tn, tf);
                     dist = 0.0f;
-                    lim  = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
-                    // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
-                    if (!JULIA && (LY != 0 || S.sun_clear)) lim = fminf(lim, sun_clear_at<LY>(S, o));
+#if VP_SUN_NO_SLAB
+                    // With a sun-clear table the slab test is redundant: the table ends the walk where the last medium
+                    // toward the sun ends, and a step beyond the box reads density 0 (range test of the fetch) -- a no-op.
+                    if (!JULIA && LY != 0)
+                        lim = sun_clear_at<LY>(S, o);
+                    else
+#endif
+                    {
+                        float tn, tf;
+                        box_slabs_inv(S, o, S.sun_inv, tn, tf);
+                        lim = (tf > tn && tf >= 1e-3f) ? tf : 0.0f;
+                        // exact vacuum clip: beyond sun_clear no medium is left on the way to the sun
+                        if (!JULIA && (LY != 0 || S.sun_clear)) lim = fminf(lim, sun_clear_at<LY>(S, o));
+                    }
                     st   = kModeStep | kShadow;
                 }
             }

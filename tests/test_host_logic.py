@@ -47,6 +47,12 @@ def test_frames_for_rank_partitions_the_frames(vp, n, world):
     assert sorted(seen) == list(range(10, 10 + n))
 
 
+def test_split_frames_strong_scaling(vp):
+    for total, world in ((256, 8), (4096, 8), (7, 4), (3, 8)):
+        parts = vp.split_frames(total, world)
+        assert sum(parts) == total and max(parts) - min(parts) <= 1
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -310,6 +310,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--shard-opacity", type=int, default=1, help="N > 1: each rank sweeps 1/N of the sun-opacity table, ncclAllGather (0: every rank builds all of it)")
     ap.add_argument("--truth-spp", type=int, default=4096, help="spp of the reference-kernel ground truth of the time-to-RMSE leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -375,12 +376,16 @@ def main():
     r.copy_inv_view_matrix(view)
     r.sync()
     tb.append(time.perf_counter())
-    r.precompute_opacity(sun_dir)
+    if world > 1:
+        # the library's own NCCL communicator (C ABI); torch.distributed only carries the unique id and the barriers
+        vp.init_nccl_from_torch(r)
+    tb.append(time.perf_counter())
+    r.precompute_opacity(sun_dir, sharded=world > 1 and args.shard_opacity != 0)  # N > 1: each rank sweeps 1/N of the table, all-gather over NVLink
     r.sync()
     tb.append(time.perf_counter())
     t_setup = time.perf_counter() - t_setup
     setup_breakdown = {"volume_bounds_octets_s": round(tb[1] - tb[0], 3), "env_sun_tables_s": round(tb[2] - tb[1], 3),
-                       "opacity_s": round(tb[3] - tb[2], 3)}
+                       "nccl_comm_init_s": round(tb[3] - tb[2], 3), "opacity_s": round(tb[4] - tb[3], 3)}
     opacity_ms = r.opacity_build_ms()
     stats = r.volume_stats() if dims is not None else {}
     P = workload_param(vp, W, H, over)
@@ -390,8 +395,6 @@ def main():
     stream = main_stream.cuda_stream
     total = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)  # the image (root; N = 1: the accumulator itself)
     if world > 1:
-        # the library's own NCCL communicator (C ABI); torch.distributed only carries the unique id and the barriers
-        vp.init_nccl_from_torch(r)
         bufs = [torch.zeros(H, W, 4, device="cuda", dtype=torch.float32) for _ in range(2)]
         side = torch.cuda.Stream()
         ev_render = [torch.cuda.Event() for _ in range(2)]

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <algorithm>
@@ -78,6 +79,33 @@ bool env_flag(const char* name)
     const char* v = getenv(name);
     return v && atoi(v) != 0;
 }
+// cudaMalloc of the large pools, with the host time it took on stderr when VOLPATH_TIMING=1 (multi-process setups)
+template <class T>
+cudaError_t big_malloc(const char* what, T** p, size_t bytes)
+{
+    static const bool   timing = env_flag("VOLPATH_TIMING");
+    const auto          t0     = std::chrono::steady_clock::now();
+    const cudaError_t   e      = cudaMalloc((void**)p, bytes ? bytes : 32);
+    if (timing)
+        fprintf(stderr, "volpath: cudaMalloc %-12s %8.2f GB  %7.1f ms\n", what, bytes * 1e-9,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    return e;
+}
+struct StageTimer
+{
+    const char* what;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit StageTimer(const char* w) : what(w) {}
+    ~StageTimer()
+    {
+        static const bool timing = env_flag("VOLPATH_TIMING");
+        if (timing)
+        {
+            cudaDeviceSynchronize();
+            fprintf(stderr, "volpath: stage %-24s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    }
+};
 }  // namespace
 
 struct vp_context
@@ -418,10 +446,15 @@ static int build_from_dense_impl(vp_context* c, int nx, int ny, int nz, int stor
     // 3. octet pool
     const size_t ob = store_voxel == kF32 ? 32 : (store_voxel == kF16 ? 16 : 8);
     c->octet_bytes  = (size_t)c->n_slots * kBrickCells * ob;
-    VP_CUDA(cudaMalloc(&c->octets, c->octet_bytes ? c->octet_bytes : 32));
+    VP_CUDA(big_malloc("octets", &c->octets, c->octet_bytes));
+    StageTimer st_oct("fill octets");
     VP_CUDA(launch_fill_octets(c->dense, nx, ny, nz, S.nbx, S.nby, c->slot_brick, c->n_slots, c->octets, store_voxel, 0));
     VP_CUDA(cudaDeviceSynchronize());
-    if (!keep_dense) dev_free(c->dense);
+    if (!keep_dense)
+    {
+        StageTimer st_free("free dense");
+        dev_free(c->dense);
+    }
     if (c->bounds_cell)
     {
         // vacuum jump distances (breadth-first dilation over the bound cells, up to 63 cells)
@@ -626,8 +659,11 @@ int vp_generate_cloud(vp_context* c, int nx, int ny, int nz, unsigned int seed, 
     VP_CUDA(cudaSetDevice(c->device));
     free_volume(c);
     const size_t N = (size_t)nx * ny * nz;
-    VP_CUDA(cudaMalloc(&c->dense, N * sizeof(float)));
-    VP_CUDA(launch_fbm_cloud(c->dense, nx, ny, nz, seed, 0));
+    VP_CUDA(big_malloc("dense", &c->dense, N * sizeof(float)));
+    {
+        StageTimer st_cloud("fbm cloud");
+        VP_CUDA(launch_fbm_cloud(c->dense, nx, ny, nz, seed, 0));
+    }
     set_box(c, nx, ny, nz, boxmin3, boxmax3);
     return build_from_dense(c, nx, ny, nz, store_voxel, bounds_flags, keep_dense);
 }
@@ -750,7 +786,8 @@ int vp_set_inv_view(vp_context* c, const float* m12)
     return VP_OK;
 }
 
-int vp_precompute_opacity(vp_context* c, const float* dir3)
+static int all_gather_bytes(vp_context* c, void* buf, size_t bytes_per_rank);
+static int precompute_opacity_impl(vp_context* c, const float* dir3, bool sharded)
 {
     if (!c || !dir3) return fail(VP_ERR_INVALID, "vp_precompute_opacity: bad arguments");
     if (!c->have_volume) return fail(VP_ERR_NO_VOLUME, "vp_precompute_opacity: no volume");
@@ -783,10 +820,18 @@ int vp_precompute_opacity(vp_context* c, const float* dir3)
     {
         int K = 64;
         if (const char* k = getenv("VOLPATH_OPACITY_K")) K = atoi(k) > 0 ? atoi(k) : K;
-        cudaError_t e = cudaMalloc(&c->opacity_oct, slots * kBrickCells * 16);
-        if (e == cudaSuccess) e = launch_opacity_octets(c->S, c->slot_brick, c->n_slots, c->opacity_oct, dir, K, 0);
+        // sharded build (multi-GPU hosts, volume replicated): every rank sweeps the slots [r, r + 1) * per of the table and
+        // an in-place ncclAllGather over NVLink hands everybody the rest (the checkpoint slabs are cheap and replicated)
+        const int    G   = sharded && c->nccl_comm ? c->nccl_ranks : 1;
+        const size_t per = (slots + G - 1) / G;
+        cudaError_t  e   = big_malloc("opacity_oct", &c->opacity_oct, per * G * kBrickCells * 16);
+        StageTimer   st_op("opacity sweep");
+        const uint32_t b0 = G > 1 ? (uint32_t)std::min<size_t>(per * c->nccl_rank, c->n_slots) : 0u;
+        const uint32_t b1 = G > 1 ? (uint32_t)std::min<size_t>(per * (c->nccl_rank + 1), c->n_slots) : c->n_slots;
+        if (e == cudaSuccess) e = launch_opacity_octets(c->S, c->slot_brick, c->n_slots, c->opacity_oct, dir, K, 0, b0, b1);
         if (e != cudaSuccess) rc = fail((int)e, "vp_precompute_opacity (swept octets): %s", cudaGetErrorString(e));
         c->launches += 2;
+        if (rc == VP_OK && G > 1) rc = all_gather_bytes(c, c->opacity_oct, per * kBrickCells * 16);
     }
     cudaEventRecord(t1, 0);
     cudaError_t e = cudaDeviceSynchronize();
@@ -806,6 +851,9 @@ int vp_precompute_opacity(vp_context* c, const float* dir3)
     c->S.opacity_oct  = c->opacity_oct;
     return VP_OK;
 }
+
+int vp_precompute_opacity(vp_context* c, const float* dir3) { return precompute_opacity_impl(c, dir3, false); }
+int vp_precompute_opacity_sharded(vp_context* c, const float* dir3) { return precompute_opacity_impl(c, dir3, true); }
 
 static int render_on(vp_context* c, void* d_sum, int first_frame, int n_frames, int frame_stride, const vp_param* p, int mode,
                      cudaStream_t st);
@@ -1099,6 +1147,7 @@ struct NcclApi
     int (*CommDestroy)(void*)                                                                 = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t)             = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t)               = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t)                    = nullptr;
     int (*GroupStart)()                                                                       = nullptr;
     int (*GroupEnd)()                                                                         = nullptr;
     const char* (*GetErrorString)(int)                                                        = nullptr;
@@ -1125,6 +1174,7 @@ NcclApi& nccl()
         VP_SYM(CommDestroy, "ncclCommDestroy");
         VP_SYM(Reduce, "ncclReduce");
         VP_SYM(AllReduce, "ncclAllReduce");
+        VP_SYM(AllGather, "ncclAllGather");
         VP_SYM(GroupStart, "ncclGroupStart");
         VP_SYM(GroupEnd, "ncclGroupEnd");
         VP_SYM(GetErrorString, "ncclGetErrorString");
@@ -1142,6 +1192,15 @@ constexpr int kNcclFloat = 7, kNcclSum = 0;
         if (r_ != 0) return fail(20000 + r_, "%s: %s", #x, nccl().GetErrorString ? nccl().GetErrorString(r_) : "?"); \
     } while (0)
 }  // namespace
+
+// in-place all-gather of `bytes_per_rank` bytes per rank into buf (rank r's share already sits at offset r * bytes_per_rank)
+static int all_gather_bytes(vp_context* c, void* buf, size_t bytes_per_rank)
+{
+    if (!c->nccl_comm || !nccl().AllGather) return fail(VP_ERR_UNSUPPORTED, "all-gather needs vp_nccl_init (and an NCCL with ncclAllGather)");
+    VP_NCCL(nccl().AllGather((const char*)buf + (size_t)c->nccl_rank * bytes_per_rank, buf, bytes_per_rank, /*ncclChar*/ 0, c->nccl_comm, 0));
+    c->launches++;
+    return VP_OK;
+}
 
 int vp_nccl_available(void)
 {

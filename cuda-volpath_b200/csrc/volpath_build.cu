@@ -634,9 +634,10 @@ __global__ void __launch_bounds__(256) k_opacity_octets(const __grid_constant__ 
 }
 
 cudaError_t launch_opacity_octets(const Scene& S, const uint32_t* slot_brick, uint32_t n_slots, void* octets_f16, float3 light_dir,
-                                  int K, cudaStream_t stream)
+                                  int K, cudaStream_t stream, uint32_t slot_begin, uint32_t slot_end)
 {
-    if (n_slots == 0) return cudaSuccess;
+    if (slot_end > n_slots) slot_end = n_slots;
+    if (n_slots == 0 || slot_begin >= slot_end) return cudaSuccess;
     const float ax = fabsf(light_dir.x), ay = fabsf(light_dir.y), az = fabsf(light_dir.z);
     TauSweep W{};
     W.axis     = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
@@ -666,10 +667,14 @@ cudaError_t launch_opacity_octets(const Scene& S, const uint32_t* slot_brick, ui
         }
         W.planes = planes;
     }
-    const unsigned g = n_slots < sms(32) ? n_slots : (unsigned)sms(32);
-    if (S.voxel_type == kF32) k_opacity_octets<kF32><<<g, 256, 0, stream>>>(S, W, slot_brick, n_slots, (uint4*)octets_f16, light_dir);
-    else if (S.voxel_type == kF16) k_opacity_octets<kF16><<<g, 256, 0, stream>>>(S, W, slot_brick, n_slots, (uint4*)octets_f16, light_dir);
-    else k_opacity_octets<kU8><<<g, 256, 0, stream>>>(S, W, slot_brick, n_slots, (uint4*)octets_f16, light_dir);
+    // slots [slot_begin, slot_end): the whole table, or this rank's share of a sharded build (vp_precompute_opacity_sharded)
+    const uint32_t  mine = slot_end - slot_begin;
+    const unsigned  g    = mine < sms(32) ? mine : (unsigned)sms(32);
+    const uint32_t* sb   = slot_brick + slot_begin;
+    uint4*          out  = (uint4*)octets_f16 + (size_t)slot_begin * kBrickCells;
+    if (S.voxel_type == kF32) k_opacity_octets<kF32><<<g, 256, 0, stream>>>(S, W, sb, mine, out, light_dir);
+    else if (S.voxel_type == kF16) k_opacity_octets<kF16><<<g, 256, 0, stream>>>(S, W, sb, mine, out, light_dir);
+    else k_opacity_octets<kU8><<<g, 256, 0, stream>>>(S, W, sb, mine, out, light_dir);
     cudaError_t e = cudaGetLastError();
     if (planes)
     {

@@ -47,7 +47,7 @@ cudaError_t launch_precompute_opacity(const Scene& S, const uint32_t* slot_brick
                                       float3 light_dir, cudaStream_t stream);
 // production table: swept build (checkpoint slabs every K voxels along the sun's dominant axis), fp16 octets per cell
 cudaError_t launch_opacity_octets(const Scene& S, const uint32_t* slot_brick, uint32_t n_slots, void* octets_f16, float3 light_dir,
-                                  int K, cudaStream_t stream);
+                                  int K, cudaStream_t stream, uint32_t slot_begin = 0, uint32_t slot_end = 0xffffffffu);
 cudaError_t launch_gather_opacity_oct(const Scene& S, float* dense_out, cudaStream_t stream);
 cudaError_t launch_vacuum_jumps(float2* bounds_cell, uint8_t* tmp, int ncx, int ncy, int ncz, int kmax, int margin,
                                 float cell_world, cudaStream_t stream);

@@ -60,7 +60,9 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #define VP_INLINE_SEG 0
 #endif
 #ifndef VP_SUN_NO_SLAB
-#define VP_SUN_NO_SLAB 1  // sun shadow walks end at the sun-clear distance alone (exact; +0.7 % at full C2, profiles/README.md)
+#define VP_SUN_NO_SLAB 0  // experiment: sun shadow walks ended by the sun-clear distance alone (+0.7 % at full C2) -- NOT exact when medium
+                          // touches the box wall: clamp addressing extends the border voxels half a voxel beyond the box
+                          // (caught by test_tiny_full_box_grid_sun_clear_clip_is_conservative); off
 #endif
 #ifndef VP_SEG_ITERS
 #define VP_SEG_ITERS 0  // 0: the segment block loops over vacuum jumps until medium or exit
@@ -623,7 +625,8 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
 #if VP_SUN_NO_SLAB
                     // With a sun-clear table the slab test is redundant: the table ends the walk where the last medium
                     // toward the sun ends, and a step beyond the box reads density 0 (range test of the fetch) -- a no-op.
-                    if (!JULIA && LY != 0)
+                    // (The rule must not depend on the layout variant: the number of draws a walk consumes follows from it.)
+                    if (!JULIA && (LY != 0 || S.sun_clear))
                         lim = sun_clear_at<LY>(S, o);
                     else
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "vp_get_envmap": (c_int, [c_vp, c_fp, ctypes.POINTER(c_int)]),
     "vp_set_inv_view": (c_int, [c_vp, c_fp]),
     "vp_precompute_opacity": (c_int, [c_vp, c_fp]),
+    "vp_precompute_opacity_sharded": (c_int, [c_vp, c_fp]),
     "vp_free_volume": (c_int, [c_vp]),
     "vp_render": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.POINTER(Param), c_int, c_vp]),
     "vp_render_to_host": (c_int, [c_vp, c_vp, c_int, c_int, c_int, ctypes.POINTER(Param), c_int]),

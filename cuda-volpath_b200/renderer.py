@@ -86,9 +86,12 @@ class Renderer:
         assert m.size == 12
         _l.check(self.L.vp_set_inv_view(self.h, _fp(m)))
 
-    def precompute_opacity(self, sun_dir):
+    def precompute_opacity(self, sun_dir, sharded=False):
+        """precompute_opacity (K.cu:526); sharded=True (after nccl_init, collective): every rank builds 1/G of the
+        production table and an all-gather over NVLink completes it."""
         d = np.ascontiguousarray(sun_dir, np.float32)
-        _l.check(self.L.vp_precompute_opacity(self.h, _fp(d)))
+        fn = self.L.vp_precompute_opacity_sharded if sharded else self.L.vp_precompute_opacity
+        _l.check(fn(self.h, _fp(d)))
 
     def free_cuda_buffers(self):
         _l.check(self.L.vp_free_volume(self.h))

@@ -36,6 +36,10 @@ def init_nccl_from_torch(renderer, group=None):
     t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
     dist.broadcast(t, src=0, group=group)
     renderer.nccl_init(world, rank, bytes(t.cpu().tolist()))
+    # NCCL connects its rings lazily inside the first collective (hundreds of ms): pay that here, with one float4
+    warm = torch.zeros(4, dtype=torch.float32, device="cuda")
+    renderer.reduce_nccl(warm.data_ptr(), warm.data_ptr() if rank == 0 else None, 1, root=0, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
     return rank, world
 
 

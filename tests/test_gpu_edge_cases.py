@@ -143,3 +143,26 @@ def test_volume_reupload_and_filter_switch_keep_the_context_consistent(R, oracle
     R.free_cuda_buffers()
     with pytest.raises(vp.VolpathError, match="no volume"):
         R.render(P, 0, 1, mode=vp.MODE_FAST)
+
+
+def test_checkpoint_resume_on_the_gpu_path(tmp_path, R, oracle, vp):
+    """SURVEY.md 8f row 3 on the CUDA path: a sample is addressed by (pixel, frame), so resuming a checkpointed float4 sum
+    continues the SAME render.  Parity mode adds frames in order inside a thread: bit-identical to the uninterrupted
+    render.  The production renderer accumulates with atomics: scatter counts identical, rgb up to fp32 order."""
+    vol = small_cloud(oracle, (48, 32, 56))
+    setup_renderer(R, vp, vol, False, True)
+    P = vp.default_param(64, 48)
+    P.density = 200.0
+    for mode, exact in ((vp.MODE_PARITY, True), (vp.MODE_FAST, False)):
+        full = R.render(P, 0, 9, mode=mode)
+        part = R.render(P, 0, 4, mode=mode)
+        p = str(tmp_path / ("ck%d.npz" % mode))
+        vp.io.save_checkpoint(p, part, 4, P)
+        acc, nxt, pb = vp.io.load_checkpoint(p)
+        assert nxt == 4 and bytes(pb) == bytes(P)
+        resumed = R.render(P, nxt, 5, mode=mode, accum=acc)
+        assert np.array_equal(resumed[..., 3], full[..., 3])
+        if exact:
+            assert np.array_equal(resumed.view(np.uint32), full.view(np.uint32))
+        else:
+            assert np.allclose(resumed[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)

@@ -114,6 +114,20 @@ def test_nccl_reduce_through_the_c_abi_single_rank():
     if not r.L.vp_nccl_available():
         pytest.skip("libnccl.so.2 not loadable")
     r.nccl_init(1, 0, r.nccl_unique_id())
+    # the sharded opacity build degenerates to the plain one on a one-rank communicator
+    import numpy as np
+
+    from oraclelib import Oracle
+
+    vol = Oracle().fbm_cloud(48, 32, 56, seed=1)
+    r.init_cuda(vol, False)
+    r.set_texture_filter_mode(True)
+    sun = np.array([0.0, 0.951057, -0.309017], np.float32)
+    r.set_sun(sun, np.ones(3, np.float32))
+    r.precompute_opacity(sun)
+    plain = r.opacity_fast()
+    r.precompute_opacity(sun, sharded=True)
+    assert np.array_equal(plain, r.opacity_fast()) and plain.max() > 0
     a = torch.rand(1000, 4, device="cuda")
     b = torch.zeros_like(a)
     s = torch.cuda.current_stream().cuda_stream

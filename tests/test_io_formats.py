@@ -98,3 +98,53 @@ def test_hdr_reader_handles_repeat_runs(tmp_path, vp):
     assert np.allclose(img[1, 3], np.array([128, 64, 32]) * 2.0 ** (129 - 136))
     assert np.allclose(img[0, 2], np.array([10, 20, 30]) * 2.0 ** (130 - 136))
     assert np.allclose(img[0, 7], np.array([200, 100, 50]) * 2.0 ** (127 - 136))
+
+
+# ---- pinned by the reference's own file-format code (tests/golden/io_golden.npz, made by tests/golden/make_io_golden.py
+# ---- from src/image.cpp and the loader lines of src/volumeRender.cpp compiled by oracle/build_ref.py) -------------------
+@pytest.fixture(scope="module")
+def io_golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io_golden.npz"))
+
+
+def test_ppm_and_hdr_bytes_equal_the_reference_writers(tmp_path, vp, io_golden):
+    """Image::dump_ppm / Image::dump_hdr (image.cpp:20-111): byte-identical files for the same float4 image."""
+    img = io_golden["image"]
+    p = str(tmp_path / "a.ppm")
+    vp.io.dump_ppm(p, img)
+    assert np.array_equal(np.frombuffer(open(p, "rb").read(), np.uint8), io_golden["ppm_bytes"])
+    p = str(tmp_path / "a.hdr")
+    vp.io.dump_hdr(p, img)
+    assert np.array_equal(np.frombuffer(open(p, "rb").read(), np.uint8), io_golden["hdr_bytes"])
+    # and our reader takes the reference's file back within RGBE precision
+    ref_file = str(tmp_path / "ref.hdr")
+    open(ref_file, "wb").write(io_golden["hdr_bytes"].tobytes())
+    back = vp.io.load_hdr(ref_file)
+    mx = img[..., :3].max(axis=-1, keepdims=True)
+    assert np.all(np.abs(back - img[..., :3]) <= mx / 128 + 1e-30)
+
+
+def test_bin_loader_and_quantisation_rules_equal_the_reference(tmp_path, vp, io_golden):
+    """loadBinaryFile (volumeRender.cpp:915-965) and the loadVdbFile uchar rule (volumeRender.cpp:1003-1009)."""
+    p = str(tmp_path / "v.bin")
+    open(p, "wb").write(io_golden["bin_bytes"].tobytes())
+    assert np.array_equal(vp.io.load_bin(p, quantized=True), io_golden["bin_quantized"])
+    f = vp.io.load_bin(p, quantized=False)
+    assert np.array_equal(f.view(np.uint32), io_golden["bin_float"].view(np.uint32))
+    # our writer produces the file the reference's loader was given
+    vp.io.save_bin(str(tmp_path / "w.bin"), io_golden["bin_float"])
+    assert open(str(tmp_path / "w.bin"), "rb").read() == io_golden["bin_bytes"].tobytes()
+    w = io_golden["by_max_in"]
+    assert np.array_equal(vp.io.quantize_by_max(w), io_golden["by_max_out"])
+
+
+def test_gamma_resolve_equals_the_reference_tonemap(vp, io_golden):
+    """Image::scale + Image::tonemap_gamma (image.cpp:189-209) on the host; the device kernels (K.cu:2333-2362) are
+    checked against the same formula in tests/test_gpu_parity.py::test_resolve_kernels_vs_oracle."""
+    s, g = [float(v) for v in io_golden["gamma_scale"]]
+    img = io_golden["image"]
+    want = io_golden["gamma_image"]
+    got = np.power(np.clip(img[..., :3] * np.float32(s), 0, 1), np.float32(1.0 / g), dtype=np.float32)
+    assert np.allclose(got, want[..., :3], rtol=3e-6, atol=1e-7)

@@ -54,6 +54,48 @@ __device__ __forceinline__ float density_at(const Scene& S, float3 pos)
     return VT == kU8 ? r * (1.0f / 255.0f) : r;
 }
 
+// The same fetch for a walk step, plus EMPTY-BRICK SKIPPING: when the position lies in a brick that stores nothing (all
+// 9^3 voxels it touches are zero, so the trilinear density is exactly 0 in all of it), `skip` returns the distance along
+// s to the brick's exit.  Every tentative collision up to there would be a null collision with weight exactly 1 (tracking
+// without a control component) or a shadow step that cannot kill, so the walk may move to the exit without drawing:
+// an exponential walk through vacuum is memoryless -- same distribution, fewer steps.  skip = 0 otherwise.
+template <int VT, bool JULIA, int LY = 0>
+__device__ __forceinline__ float density_at_skip(const Scene& S, float3 pos, float3 s, float& skip)
+{
+    skip = 0.0f;
+    if (JULIA) return julia_density(pos);
+    if (LY == 0 && !S.linear) return density_at<VT, JULIA, LY>(S, pos);
+    float v[8];
+    float xb = fmaf(pos.x, S.vs_scale.x, S.vs_off_lin.x), yb = fmaf(pos.y, S.vs_scale.y, S.vs_off_lin.y),
+          zb = fmaf(pos.z, S.vs_scale.z, S.vs_off_lin.z);
+    float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+    int   ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    if (((unsigned)ix > (unsigned)S.nx) | ((unsigned)iy > (unsigned)S.ny) | ((unsigned)iz > (unsigned)S.nz)) return 0.0f;
+    uint32_t slot = brick_slot<LY>(S, ix, iy, iz);
+    if (slot == kEmptyBrick)
+    {
+        // exit of the brick [8b, 8b + 8) in cell' coordinates along d' = s * vs_scale
+        const float dx = s.x * S.vs_scale.x, dy = s.y * S.vs_scale.y, dz = s.z * S.vs_scale.z;
+        const float bx = (float)(ix & ~(kBrick - 1)), by = (float)(iy & ~(kBrick - 1)), bz = (float)(iz & ~(kBrick - 1));
+        const float tx = __fdividef((dx > 0.0f ? bx + (float)kBrick : bx) - xb, dx);
+        const float ty = __fdividef((dy > 0.0f ? by + (float)kBrick : by) - yb, dy);
+        const float tz = __fdividef((dz > 0.0f ? bz + (float)kBrick : bz) - zb, dz);
+        // 0 / 0 (on a face, moving parallel to it) is NaN and x / 0 is +inf: fminf drops the NaN, keeps the finite exits
+        skip = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+        return 0.0f;
+    }
+    load_octet<VT>(S.octets, cell_in_slot(slot, ix, iy, iz), v);
+    float a = xb - fx, b = yb - fy, g = zb - fz;
+    float c00 = fmaf(a, v[1] - v[0], v[0]);
+    float c10 = fmaf(a, v[3] - v[2], v[2]);
+    float c01 = fmaf(a, v[5] - v[4], v[4]);
+    float c11 = fmaf(a, v[7] - v[6], v[6]);
+    float c0  = fmaf(b, c10 - c00, c00);
+    float c1  = fmaf(b, c11 - c01, c01);
+    float r   = fmaf(g, c1 - c0, c0);
+    return VT == kU8 ? r * (1.0f / 255.0f) : r;
+}
+
 // opacity table of the production renderers: the cell's 8 corner values sit in one 16-byte fp16 octet (same slot and
 // cell addressing as the density octets), so the lookup of K.cu:2183-2195 is one directory load + ONE vector load;
 // trilinear weights as the texture unit defines them (K.cu:541-542: always linear), FMA lerps

@@ -59,6 +59,9 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #ifndef VP_INLINE_SEG
 #define VP_INLINE_SEG 0
 #endif
+#ifndef VP_BRICK_SKIP
+#define VP_BRICK_SKIP 0
+#endif
 #ifndef VP_SUN_NO_SLAB
 #define VP_SUN_NO_SLAB 0  // experiment: sun shadow walks ended by the sun-clear distance alone (+0.7 % at full C2) -- NOT exact when medium
                           // touches the box wall: clamp addressing extends the border voxels half a voxel beyond the box
@@ -376,7 +379,15 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 float      den  = 0.0f;
                 if (!past)
                 {
+#if VP_BRICK_SKIP
+                    float skip;
+                    den = density_at_skip<VT, JULIA, LY>(S, pos, s, skip) * dens;
+                    // empty brick: move to its exit without drawing (exact: see density_at_skip); not in a decomposition
+                    // segment, whose control component makes a zero-density step a real event
+                    if (sigc == 0.0f || (st & kShadow)) dist += skip;
+#else
                     den = density_at<VT, JULIA, LY>(S, pos) * dens;
+#endif
                     if (STATS)
                     {
                         if (st & kShadow) c_shadow++; else c_track++;

@@ -96,6 +96,17 @@ __device__ __forceinline__ float density_at_skip(const Scene& S, float3 pos, flo
     return VT == kU8 ? r * (1.0f / 255.0f) : r;
 }
 
+// When the skip pays: it costs ~25 instructions in a divergent branch of the step block, and saves the further no-op steps
+// inside the same empty brick -- about (brick edge) x (majorant) of them.  Measured at full C2 dims (profiles/README.md):
+// density 800 (6 expected no-op steps per brick crossing at d_max = 1): +-0 %; density 3000 (24): +12.7 %; chromatic media
+// lose (the 3-channel step spills with it).  Rule, the same for every production kernel so that they keep rendering the
+// same samples: gray media with density x sigma_t x brick edge >= 12.
+__host__ __device__ inline bool use_brick_skip(const Scene& S, float density, float max_sig_t, bool gray)
+{
+    const float vmax = fmaxf(S.vs_scale.x, fmaxf(S.vs_scale.y, S.vs_scale.z));
+    return gray && !S.julia && S.linear && density * max_sig_t * ((float)kBrick / vmax) >= 12.0f;
+}
+
 // opacity table of the production renderers: the cell's 8 corner values sit in one 16-byte fp16 octet (same slot and
 // cell addressing as the density octets), so the lookup of K.cu:2183-2195 is one directory load + ONE vector load;
 // trilinear weights as the texture unit defines them (K.cu:541-542: always linear), FMA lerps

@@ -59,9 +59,6 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #ifndef VP_INLINE_SEG
 #define VP_INLINE_SEG 0
 #endif
-#ifndef VP_BRICK_SKIP
-#define VP_BRICK_SKIP 0
-#endif
 #ifndef VP_SUN_NO_SLAB
 #define VP_SUN_NO_SLAB 0  // experiment: sun shadow walks ended by the sun-clear distance alone (+0.7 % at full C2) -- NOT exact when medium
                           // touches the box wall: clamp addressing extends the border voxels half a voxel beyond the box
@@ -146,13 +143,18 @@ struct ColdF
     __device__ __forceinline__ void operator=(float v) const { *p = v; }
 };
 
-template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS, int LY>
+template <int VT, bool JULIA, bool GRAY, bool MIS, bool STATS, int LYX>
 __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_render_fast(const __grid_constant__ Scene S, float4* __restrict__ d_sum,
                                                                   int first_frame, int n_frames, int frame_stride,
                                                                   const __grid_constant__ vp_param P,
                                                                   unsigned long long* __restrict__ d_work,
-                                                                  unsigned long long* __restrict__ d_stats, uint32_t claim)
+                                                                  unsigned long long* __restrict__ d_stats, uint32_t claim, int skip_rt)
 {
+    // LYX = layout (0 generic, 1 small volume, 2 large volume) + 2 when empty-brick skipping is compiled in (3, 4);
+    // the generic kernel takes the same decision from its argument
+    constexpr int  LY    = LYX >= 3 ? LYX - 2 : LYX;
+    constexpr bool kSkip = LYX >= 3;
+    const bool     skip_on = kSkip || (LYX == 0 && skip_rt != 0);
     const uint32_t lane    = threadIdx.x & 31;
     const uint32_t tiles_x = (P.width + 7) >> 3, tiles_y = (P.height + 3) >> 2;
     const unsigned long long n_items = (unsigned long long)tiles_x * tiles_y * 32ull * (unsigned long long)n_frames;
@@ -379,15 +381,16 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                 float      den  = 0.0f;
                 if (!past)
                 {
-#if VP_BRICK_SKIP
-                    float skip;
-                    den = density_at_skip<VT, JULIA, LY>(S, pos, s, skip) * dens;
-                    // empty brick: move to its exit without drawing (exact: see density_at_skip); not in a decomposition
-                    // segment, whose control component makes a zero-density step a real event
-                    if (sigc == 0.0f || (st & kShadow)) dist += skip;
-#else
-                    den = density_at<VT, JULIA, LY>(S, pos) * dens;
-#endif
+                    if (!JULIA && GRAY && (kSkip || LYX == 0) && skip_on)
+                    {
+                        float skip;
+                        den = density_at_skip<VT, JULIA, LY>(S, pos, s, skip) * dens;
+                        // empty brick: move to its exit without drawing (exact: see density_at_skip); not in a decomposition
+                        // segment, whose control component makes a zero-density step a real event
+                        if (sigc == 0.0f || (st & kShadow)) dist += skip;
+                    }
+                    else
+                        den = density_at<VT, JULIA, LY>(S, pos) * dens;
                     if (STATS)
                     {
                         if (st & kShadow) c_shadow++; else c_track++;
@@ -691,14 +694,23 @@ static cudaError_t launch_fast_t(const Scene& S, float4* d_sum, int first_frame,
         if (S.brick_table && !S.bounds_half && !S.sun_clear_half) ly = 1;
         if (!S.brick_table && S.bounds_half && S.sun_clear_half) ly = 2;
     }
+    // empty-brick skipping: one rule for every production kernel (use_brick_skip), compiled in for the two layouts
+    const int skip = use_brick_skip(S, P.density, fmaxf(P.sigma_t.x, fmaxf(P.sigma_t.y, P.sigma_t.z)), GRAY) ? 1 : 0;
+#define VP_LAUNCH(JJ, MM, SS, LL) \
+    k_render_fast<VT, JJ, GRAY, MM, SS, LL><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, SS ? d_stats : nullptr, claim, skip)
     if (d_stats)
-        k_render_fast<VT, JULIA, GRAY, MIS, true, 0><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, claim);
+        VP_LAUNCH(JULIA, MIS, true, 0);
     else if (!JULIA && !MIS && ly == 1)
-        k_render_fast<VT, false, GRAY, false, false, 1><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
+    {
+        if (GRAY && skip) VP_LAUNCH(false, false, false, 3); else VP_LAUNCH(false, false, false, 1);
+    }
     else if (!JULIA && !MIS && ly == 2)
-        k_render_fast<VT, false, GRAY, false, false, 2><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
+    {
+        if (GRAY && skip) VP_LAUNCH(false, false, false, 4); else VP_LAUNCH(false, false, false, 2);
+    }
     else
-        k_render_fast<VT, JULIA, GRAY, MIS, false, 0><<<grid, kFastThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, claim);
+        VP_LAUNCH(JULIA, MIS, false, 0);
+#undef VP_LAUNCH
     return cudaGetLastError();
 }
 

@@ -65,7 +65,7 @@ template <int VT, bool JULIA, bool GRAY, bool STATS, bool MIS>
 __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant__ Scene S, float4* __restrict__ d_sum, int first_frame,
                                                           int n_frames, int frame_stride, const __grid_constant__ vp_param P,
                                                           unsigned long long* __restrict__ d_work,
-                                                          unsigned long long* __restrict__ d_stats)
+                                                          unsigned long long* __restrict__ d_stats, int skip_rt)
 {
     __shared__ float smem[kWarps * warp_smem_words(MIS)];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -260,7 +260,18 @@ __global__ void __launch_bounds__(kThreads) k_render_wave(const __grid_constant_
                     const bool past = dist >= lim;
                     float3     pos  = o + s * (past ? lim : dist);
                     float      den  = 0.0f;
-                    if (!past) den = density_at<VT, JULIA>(S, pos) * dens;
+                    if (!past)
+                    {
+                        if (!JULIA && GRAY && skip_rt)
+                        {
+                            // empty-brick skipping, the megakernel's rule and arithmetic (use_brick_skip, density_at_skip)
+                            float skip;
+                            den = density_at_skip<VT, JULIA>(S, pos, s, skip) * dens;
+                            if (sigc == 0.0f || (st & kShadow)) dist += skip;
+                        }
+                        else
+                            den = density_at<VT, JULIA>(S, pos) * dens;
+                    }
                     if (st & kShadow)
                     {
                         if (!past)
@@ -549,10 +560,11 @@ static cudaError_t launch_wave_t(const Scene& S, float4* d_sum, int first_frame,
     unsigned long long cap   = (unsigned long long)num_sms * per_sm;
     unsigned int       grid  = (unsigned int)(ctas < cap ? ctas : cap);
     if (grid < 1) grid = 1;
+    const int skip = use_brick_skip(S, P.density, fmaxf(P.sigma_t.x, fmaxf(P.sigma_t.y, P.sigma_t.z)), GRAY) ? 1 : 0;
     if (d_stats)
-        wave::k_render_wave<VT, JULIA, GRAY, true, MIS><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats);
+        wave::k_render_wave<VT, JULIA, GRAY, true, MIS><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, d_stats, skip);
     else
-        wave::k_render_wave<VT, JULIA, GRAY, false, MIS><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr);
+        wave::k_render_wave<VT, JULIA, GRAY, false, MIS><<<grid, wave::kThreads, 0, stream>>>(S, d_sum, first_frame, n_frames, frame_stride, P, d_work, nullptr, skip);
     return cudaGetLastError();
 }
 

@@ -310,7 +310,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--shard-opacity", type=int, default=1, help="N > 1: each rank sweeps 1/N of the sun-opacity table, ncclAllGather (0: every rank builds all of it)")
+    ap.add_argument("--shard-opacity", type=int, default=0,
+                    help="N > 1: each rank sweeps 1/N of the sun-opacity table + ncclAllGather (needs the communicator first, so the NCCL "
+                         "bootstrap no longer overlaps the volume build; default 0: every rank builds all of it, 0.55 s)")
+    ap.add_argument("--reduce", default="end", choices=["end", "step"],
+                    help="N > 1: 'end' = every rank accumulates all its frames, ONE vp_reduce_nccl at the end of the timed region "
+                         "(the NCCL bootstrap, seconds at 8 ranks, overlaps setup and rendering); 'step' = one reduce per step on a "
+                         "side stream, overlapped with the next step's render (progressive image on the root)")
+    ap.add_argument("--render-streams", type=int, default=2, choices=[1, 2],
+                    help="consecutive steps alternate between this many streams, so the tail of one launch overlaps the next launch")
     ap.add_argument("--truth-spp", type=int, default=4096, help="spp of the reference-kernel ground truth of the time-to-RMSE leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -363,6 +371,18 @@ def main():
     env, sun_dir, sun_power, view = scene_inputs(vp)
     t_setup = time.perf_counter()
     store = vp.VOXEL_F32 if args.store == "f32" else vp.VOXEL_F16
+    # The library's own NCCL communicator (C ABI).  torch.distributed only carries the 128-byte id (through its TCP store)
+    # and the barriers.  ncclCommInitRank plus NCCL's lazy ring set-up cost seconds at 8 ranks, so the bootstrap runs in a
+    # background thread beside the volume build -- and, with --reduce end, beside the rendering.
+    nccl_thread, nccl_info = None, {}
+    if world > 1:
+        def _nccl_boot():
+            t0 = time.perf_counter()
+            vp.init_nccl_via_store(r, rank, world)
+            nccl_info["s"] = time.perf_counter() - t0
+
+        nccl_thread = threading.Thread(target=_nccl_boot, daemon=True)
+        nccl_thread.start()
     tb = [time.perf_counter()]
     if dims is None:
         r.set_julia()
@@ -376,16 +396,15 @@ def main():
     r.copy_inv_view_matrix(view)
     r.sync()
     tb.append(time.perf_counter())
-    if world > 1:
-        # the library's own NCCL communicator (C ABI); torch.distributed only carries the unique id and the barriers
-        vp.init_nccl_from_torch(r)
     tb.append(time.perf_counter())
-    r.precompute_opacity(sun_dir, sharded=world > 1 and args.shard_opacity != 0)  # N > 1: each rank sweeps 1/N of the table, all-gather over NVLink
+    if world > 1 and args.shard_opacity:
+        nccl_thread.join()  # the sharded sweep is a collective: it needs the communicator now
+    r.precompute_opacity(sun_dir, sharded=world > 1 and args.shard_opacity != 0)
     r.sync()
     tb.append(time.perf_counter())
     t_setup = time.perf_counter() - t_setup
     setup_breakdown = {"volume_bounds_octets_s": round(tb[1] - tb[0], 3), "env_sun_tables_s": round(tb[2] - tb[1], 3),
-                       "nccl_comm_init_s": round(tb[3] - tb[2], 3), "opacity_s": round(tb[4] - tb[3], 3)}
+                       "opacity_s": round(tb[4] - tb[3], 3)}
     opacity_ms = r.opacity_build_ms()
     stats = r.volume_stats() if dims is not None else {}
     P = workload_param(vp, W, H, over)
@@ -393,25 +412,33 @@ def main():
     step_frames = fps if (world == 1 or strong) else fps * world  # frames of one step, all ranks together
     main_stream = torch.cuda.current_stream()
     stream = main_stream.cuda_stream
-    total = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)  # the image (root; N = 1: the accumulator itself)
-    if world > 1:
+    # consecutive steps alternate between the render streams: the persistent grid of step k + 1 moves in as the CTAs of
+    # step k retire, so the tail of a launch (its last, longest paths) is filled with the next launch's work
+    rs = [torch.cuda.Stream() for _ in range(args.render_streams)]
+    total = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)  # N = 1 / --reduce end: this rank's accumulator; the image on the root
+    reduce_step = world > 1 and args.reduce == "step"
+    if reduce_step:
+        nccl_thread.join()
         bufs = [torch.zeros(H, W, 4, device="cuda", dtype=torch.float32) for _ in range(2)]
         side = torch.cuda.Stream()
         ev_render = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         used = [False, False]
+    torch.cuda.synchronize()
 
     def step(k):
         # global frames of step k: [k * step_frames, (k + 1) * step_frames); this rank takes every world-th one
         first, count, stride = vp.frames_for_rank(k * step_frames, step_frames, rank, world)
-        if world == 1:
-            r.render_kernel(total.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
+        if not reduce_step:
+            st = rs[k % len(rs)]
+            r.render_kernel(total.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=st.cuda_stream)
             return
         b = k & 1
+        st = rs[b % len(rs)]
         if used[b]:
-            main_stream.wait_event(ev_free[b])  # its reduce (step k - 2) has drained and zeroed the buffer
-        r.render_kernel(bufs[b].data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
-        ev_render[b].record(main_stream)
+            st.wait_event(ev_free[b])  # its reduce (step k - 2) has drained and zeroed the buffer
+        r.render_kernel(bufs[b].data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=st.cuda_stream)
+        ev_render[b].record(st)
         side.wait_event(ev_render[b])
         r.reduce_nccl(bufs[b].data_ptr(), bufs[b].data_ptr() if rank == 0 else None, W * H, root=0, stream=side.cuda_stream)
         if rank == 0:
@@ -422,7 +449,10 @@ def main():
         used[b] = True
 
     def drain():
-        if world > 1:
+        # the main stream waits for everything the steps put on the other streams
+        for st in rs:
+            main_stream.wait_stream(st)
+        if reduce_step:
             for b in range(2):
                 if used[b]:
                     main_stream.wait_event(ev_free[b])
@@ -440,9 +470,15 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     e0.record()
+    for st in rs:
+        st.wait_event(e0)
     for k in range(args.warmup, args.warmup + args.steps):
         step(k)
     drain()
+    if world > 1 and not reduce_step:
+        # ONE reduce of the whole accumulator, inside the timed region (ncclReduce of W*H float4 over NVLink)
+        nccl_thread.join()
+        r.reduce_nccl(total.data_ptr(), total.data_ptr() if rank == 0 else None, W * H, root=0, stream=stream)
     e1.record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall
@@ -480,10 +516,8 @@ def main():
     for k in range(2):
         r.render_kernel(scratch.data_ptr(), first + k * step_frames, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=stream)
         kms.append(r.last_kernel_ms())
-    kernel_ms = sum(kms) / len(kms)
+    kernel_ms = sum(kms) / len(kms)  # an ISOLATED launch (CUDA events on its own stream); the timed region overlaps tails
     kernel_paths = W * H * count
-    if world == 1:
-        kernel_ms = ms / args.steps  # the timed region is exactly `steps` launches of k_render_fast: CUDA events over it
     del scratch
 
     # e2e: host-buffer call, pinned float4 sum in and out
@@ -535,9 +569,16 @@ def main():
             roof["traffic_source"] = t["source"]
     roof["algorithmic_bytes_per_launch"] = per_launch_bytes
 
+    # wall-to-image of a job that renders exactly the timed steps (no warm-up): the NCCL bootstrap runs beside setup (and,
+    # with --reduce end, beside the rendering); --reduce step needs the communicator before its first step
+    nb = nccl_info.get("s", 0.0)
+    wall_to_image = (max(t_setup_max, nb) + ms * 1e-3) if reduce_step else max(t_setup_max + ms * 1e-3, nb)
+    how = ("vp_reduce_nccl per step on a side stream, double-buffered accumulators" if reduce_step else
+           "each rank accumulates its frames, ONE vp_reduce_nccl at the end of the timed region (NCCL bootstrap in a background thread)")
     par = ("one GPU" if world == 1 else
-           "sample-index sharding x%d (%s scaling: %d frames per step %s), vp_reduce_nccl per step on a side stream, "
-           "double-buffered accumulators" % (world, "strong" if strong else "weak", step_frames, "in total" if strong else "= %d per GPU" % fps))
+           "sample-index sharding x%d (%s scaling: %d frames per step %s), %s"
+           % (world, "strong" if strong else "weak", step_frames, "in total" if strong else "= %d per GPU" % fps, how))
+    par += "; consecutive steps alternate over %d render stream(s)" % len(rs)
     line = {"metric": "path-samples/s", "value": value, "unit": "path-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (strong or world == 1) else "weak",
@@ -546,9 +587,10 @@ def main():
                        "mode": "fast (megakernel)", "store": args.store,
                        "l2": "inputs larger than L2 (octet store %.1f GB)" % (stats.get("octet_bytes", 0) / 1e9),
                        "parallelism": par, "volume": stats, "setup_s": round(t_setup_max, 2), "setup_breakdown_rank0": setup_breakdown, "opacity_build_s": round(opacity_ms * 1e-3, 3),
-                       "wall_to_image_s": round(t_setup_max + ms * 1e-3, 2),
-                       "wall_note": "setup (cloud, bricks, bounds, sun tables: per GPU, replicated) + the timed region"},
-            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "image": img_stats}
+                       "wall_to_image_s": round(wall_to_image, 2), "nccl_bootstrap_s_rank0": round(nccl_info.get("s", 0.0), 2),
+                       "wall_note": "max over ranks of setup (cloud, bricks, bounds, sun tables: per GPU, replicated) + the timed region; the NCCL "
+                                    "bootstrap (background thread) counts where it is the longer pole"},
+            "roofline": roof, "e2e": e2e, "gpu_launches": launches, "ms_per_step_region": ms / args.steps, "clocks": sampler.summary(), "image": img_stats}
     if world == 1:
         line["scaling"] = "weak"  # one GPU: per-GPU work is what it is
 

@@ -46,3 +46,21 @@ def init_nccl_from_torch(renderer, group=None):
 def split_frames(total_frames, world_size):
     """Strong scaling: `total_frames` sample indices over `world_size` ranks by interleaving; -> frames of each rank."""
     return [frames_for_rank(0, total_frames, r, world_size)[1] for r in range(world_size)]
+
+
+def init_nccl_via_store(renderer, rank, world, key="volpath_nccl_id"):
+    """The same bootstrap without any torch collective: the 128-byte id travels through torch.distributed's TCP store, so
+    this may run in a background thread while the main thread builds the volume (ncclCommInitRank + NCCL's lazy ring
+    set-up cost seconds at 8 ranks).  Ends with a one-float4 reduce on a private buffer that pays the lazy set-up."""
+    import torch.distributed as dist
+
+    store = dist.distributed_c10d._get_default_store()
+    if rank == 0:
+        store.set(key, renderer.nccl_unique_id())
+    raw = bytes(store.get(key))
+    renderer.nccl_init(world, rank, raw)
+    warm = renderer.L.vp_dev_alloc(16)
+    renderer.reduce_nccl(warm, warm if rank == 0 else None, 1, root=0, stream=None)
+    renderer.sync()
+    renderer.L.vp_dev_free(warm)
+    return rank, world

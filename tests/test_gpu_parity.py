@@ -357,6 +357,32 @@ def test_fast_renderer_statistical_parity_vs_reference_cuda_kernel(R, oracle, vp
     assert rm_fast <= 1.15 * rm_ref
 
 
+@pytest.mark.parametrize("material", [8, 4])
+def test_fast_renderer_chromatic_vs_reference_cuda_kernel(R, oracle, vp, material):
+    """Config C3 against the reference's OWN kernel (the chromatic test compared against this repo's parity
+    renderer only): `Mat` presets 8 and 4 (volumeRender.cpp:1296-1308), spectral tracking with a 3-channel throughput.
+    north_star tolerances per channel: image mean 0.5 % (+ the reference's own run-to-run noise), scatter count 1 %."""
+    ref = _ref_cuda()
+    vol = small_cloud(oracle, (96, 64, 112), seed=2)
+    env, sd, sp = vp.default_sunsky()
+    P = vp.mat(vp.default_param(160, 96), *vp.MATERIALS[material])
+    P.density = 400.0
+    spp = 512
+    setup_scene(ref, vp, vol, False, True, env=env)
+    ref.precompute_opacity(sd)
+    setup_renderer(R, vp, vol, False, True, env=env)
+    R.precompute_opacity(sd)
+    a = ref.render(P, 0, spp)
+    b = ref.render(P, spp, spp)
+    f = R.render(P, 0, 2 * spp, mode=vp.MODE_FAST)
+    assert np.isfinite(f).all()
+    for ch in range(3):
+        ma, mb, mf = a[..., ch].mean(), b[..., ch].mean(), f[..., ch].mean() / 2
+        assert abs(mf - 0.5 * (ma + mb)) <= 0.005 * ma + 2 * abs(ma - mb), (material, ch, ma, mb, mf)
+    sa, sb, sf = a[..., 3].mean(), b[..., 3].mean(), f[..., 3].mean() / 2
+    assert abs(sf - 0.5 * (sa + sb)) <= 0.01 * sa, (material, sa, sb, sf)
+
+
 def test_fast_renderer_chromatic_and_high_albedo(R, oracle, vp):
     """Configs C3 (chromatic sigma_t: spectral tracking) and C4 (albedo 0.999, deep paths) against the parity
     renderer (itself trace-checked against the reference): same tolerances as above, at smaller spp."""

@@ -551,6 +551,9 @@ static int create_impl(vp_context* c, int device)
     VP_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     set_build_sm_count(c->num_sms);
+    // measurement hook (device-wide hint): how much DRAM a random 32-byte sector read drags in (tools/sector_probe.cu)
+    if (const char* g = getenv("VOLPATH_L2_FETCH_GRANULARITY"))
+        if (atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     scene_defaults(c->S);
     const float id[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
     memcpy(c->inv_model, id, sizeof(id));

@@ -2,7 +2,7 @@
 // read (the fp32 density octet: two LDG.128 to one aligned 32-byte sector) costs in DRAM traffic on a B200 when the
 // buffer is far larger than L2.  Run under ncu and compare dram__bytes_read.sum with the bytes asked for:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o sector_probe tools/sector_probe.cu
-//   ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum ./sector_probe [GiB=16] [reads per thread=64] [bytes=32|16|64|128]
+//   ncu --metrics dram__bytes_read.sum,gpu__time_duration.sum ./sector_probe [GiB=16] [reads per thread=64] [bytes=32|16|64|128] [L2 fetch granularity hint]
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +37,10 @@ int main(int argc, char** argv)
     const size_t gib   = argc > 1 ? (size_t)atoll(argv[1]) : 16;
     const int    reads = argc > 2 ? atoi(argv[2]) : 64;
     const int    bytes = argc > 3 ? atoi(argv[3]) : 32;
+    const int    gran  = argc > 4 ? atoi(argv[4]) : 0;  // cudaLimitMaxL2FetchGranularity hint (32 / 64 / 128), 0 = leave the default
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+    size_t gran_now = 0;
+    cudaDeviceGetLimit(&gran_now, cudaLimitMaxL2FetchGranularity);
     const size_t total = gib << 30;
     uint4* buf = nullptr;
     float* out = nullptr;
@@ -59,7 +63,7 @@ int main(int argc, char** argv)
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     const double asked = (double)blocks * threads * reads * bytes;
-    printf("{\"buffer_GiB\": %zu, \"read_bytes\": %d, \"reads\": %.0f, \"bytes_asked\": %.0f, \"ms\": %.3f, \"asked_GBps\": %.1f}\n", gib, bytes,
+    printf("{\"l2_fetch_granularity\": %zu, \"buffer_GiB\": %zu, \"read_bytes\": %d, \"reads\": %.0f, \"bytes_asked\": %.0f, \"ms\": %.3f, \"asked_GBps\": %.1f}\n", gran_now, gib, bytes,
            (double)blocks * threads * reads, asked, ms, asked / ms * 1e-6);
     return cudaGetLastError() != cudaSuccess;
 }

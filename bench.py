@@ -317,6 +317,9 @@ def main():
                     help="N > 1: 'end' = every rank accumulates all its frames, ONE vp_reduce_nccl at the end of the timed region "
                          "(the NCCL bootstrap, seconds at 8 ranks, overlaps setup and rendering); 'step' = one reduce per step on a "
                          "side stream, overlapped with the next step's render (progressive image on the root)")
+    ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"],
+                    help="--reduce end: 'ipc' = vp_reduce_ipc, ONE kernel on the root sums the peers' accumulators over NVLink through "
+                         "CUDA IPC mappings (no communicator, no bootstrap); 'nccl' = vp_reduce_nccl")
     ap.add_argument("--render-streams", type=int, default=2, choices=[1, 2],
                     help="consecutive steps alternate between this many streams, so the tail of one launch overlaps the next launch")
     ap.add_argument("--truth-spp", type=int, default=4096, help="spp of the reference-kernel ground truth of the time-to-RMSE leg")
@@ -354,7 +357,7 @@ def main():
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
-    import numpy as np  # noqa: F401
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -375,7 +378,8 @@ def main():
     # and the barriers.  ncclCommInitRank plus NCCL's lazy ring set-up cost seconds at 8 ranks, so the bootstrap runs in a
     # background thread beside the volume build -- and, with --reduce end, beside the rendering.
     nccl_thread, nccl_info = None, {}
-    if world > 1:
+    use_ipc = world > 1 and args.reduce == "end" and args.transport == "ipc" and not args.shard_opacity
+    if world > 1 and not use_ipc:
         def _nccl_boot():
             t0 = time.perf_counter()
             vp.init_nccl_via_store(r, rank, world)
@@ -416,7 +420,16 @@ def main():
     # step k retire, so the tail of a launch (its last, longest paths) is filled with the next launch's work
     rs = [torch.cuda.Stream() for _ in range(args.render_streams)]
     total = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)  # N = 1 / --reduce end: this rank's accumulator; the image on the root
+    total_ptr = total.data_ptr()
     reduce_step = world > 1 and args.reduce == "step"
+    if use_ipc:
+        # peer-memory reduce: the accumulator is a plain cudaMalloc block (IPC handles need base pointers); its 64-byte
+        # handle travels to the root through torch.distributed's TCP store
+        del total
+        total_ptr = r.dev_alloc(W * H * 16)
+        store = dist.distributed_c10d._get_default_store()
+        store.set("volpath_ipc_%d" % rank, r.ipc_export(total_ptr))
+        peer_handles = [bytes(store.get("volpath_ipc_%d" % q)) for q in range(1, world)] if rank == 0 else []
     if reduce_step:
         nccl_thread.join()
         bufs = [torch.zeros(H, W, 4, device="cuda", dtype=torch.float32) for _ in range(2)]
@@ -431,7 +444,7 @@ def main():
         first, count, stride = vp.frames_for_rank(k * step_frames, step_frames, rank, world)
         if not reduce_step:
             st = rs[k % len(rs)]
-            r.render_kernel(total.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=st.cuda_stream)
+            r.render_kernel(total_ptr, first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=st.cuda_stream)
             return
         b = k & 1
         st = rs[b % len(rs)]
@@ -475,10 +488,17 @@ def main():
     for k in range(args.warmup, args.warmup + args.steps):
         step(k)
     drain()
-    if world > 1 and not reduce_step:
+    if use_ipc:
+        # ONE reduce inside the timed region: every rank's render is complete (stream sync + barrier), then one kernel on
+        # the root adds the peers' accumulators, read over NVLink through their IPC mappings, in rank order
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            r.reduce_ipc(total_ptr, peer_handles, W * H, stream=stream)
+    elif world > 1 and not reduce_step:
         # ONE reduce of the whole accumulator, inside the timed region (ncclReduce of W*H float4 over NVLink)
         nccl_thread.join()
-        r.reduce_nccl(total.data_ptr(), total.data_ptr() if rank == 0 else None, W * H, root=0, stream=stream)
+        r.reduce_nccl(total_ptr, total_ptr if rank == 0 else None, W * H, root=0, stream=stream)
     e1.record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall
@@ -502,6 +522,10 @@ def main():
     img_stats = None
     if rank == 0:
         n_img = W * H * step_frames * (args.warmup + args.steps)
+        if use_ipc:
+            host = np.empty((H, W, 4), np.float32)
+            assert r.L.vp_dev_to_host(host.ctypes.data, total_ptr, host.nbytes) == 0
+            total = torch.from_numpy(host)
         finite = torch.isfinite(total).all(dim=-1)
         rgb = torch.where(finite.unsqueeze(-1), total[..., :3], torch.zeros_like(total[..., :3]))
         img_stats = {"mean_scatters_per_path": float(total[..., 3].double().sum().item() / n_img),
@@ -574,7 +598,9 @@ def main():
     nb = nccl_info.get("s", 0.0)
     wall_to_image = (max(t_setup_max, nb) + ms * 1e-3) if reduce_step else max(t_setup_max + ms * 1e-3, nb)
     how = ("vp_reduce_nccl per step on a side stream, double-buffered accumulators" if reduce_step else
-           "each rank accumulates its frames, ONE vp_reduce_nccl at the end of the timed region (NCCL bootstrap in a background thread)")
+           ("each rank accumulates its frames, ONE vp_reduce_ipc at the end of the timed region (a kernel on the root sums the peers' "
+            "accumulators over NVLink through CUDA IPC mappings; no communicator)" if use_ipc else
+            "each rank accumulates its frames, ONE vp_reduce_nccl at the end of the timed region (NCCL bootstrap in a background thread)"))
     par = ("one GPU" if world == 1 else
            "sample-index sharding x%d (%s scaling: %d frames per step %s), %s"
            % (world, "strong" if strong else "weak", step_frames, "in total" if strong else "= %d per GPU" % fps, how))
@@ -594,6 +620,8 @@ def main():
     if world == 1:
         line["scaling"] = "weak"  # one GPU: per-GPU work is what it is
 
+    if use_ipc:
+        r.L.vp_dev_free(total_ptr)
     r.close()
     del total
     torch.cuda.empty_cache()

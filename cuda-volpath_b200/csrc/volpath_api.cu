@@ -13,6 +13,8 @@
 #include <mutex>
 #include <new>
 #include <algorithm>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "volpath_common.cuh"
@@ -164,6 +166,8 @@ struct vp_context
     cudaEvent_t         ev0 = nullptr, ev1 = nullptr;
     bool                timed = false;
     float               inv_model[12];
+    // peer accumulators opened through CUDA IPC (vp_reduce_ipc): handle bytes -> mapped pointer
+    std::vector<std::pair<std::string, void*>> ipc_open;
     void*               nccl_comm = nullptr;  // ncclComm_t of vp_nccl_init (one per context = per GPU)
     int                 nccl_rank = -1, nccl_ranks = 0;
 };
@@ -590,11 +594,13 @@ int vp_create(int device, vp_context** out)
 }
 
 int vp_nccl_destroy(vp_context* c);
+int vp_ipc_close(vp_context* c);
 int vp_destroy(vp_context* c)
 {
     if (!c) return VP_OK;
     cudaSetDevice(c->device);
     vp_nccl_destroy(c);
+    vp_ipc_close(c);
     free_volume(c);
     dev_free(c->env);
     dev_free(c->env_cdf_x);
@@ -1322,6 +1328,62 @@ int vp_reduce(vp_context** ctxs, void** d_sums, int n, int size, int root)
         VP_CUDA(launch_accumulate((float4*)d_sums[root], stage.as<float4>(), size, 0));
         ctxs[root]->launches++;
         VP_CUDA(cudaDeviceSynchronize());
+    }
+    return VP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------
+// The same reduce over PEER MEMORY, without any communicator: on one node every GPU's accumulator can be mapped into
+// the root's address space through CUDA IPC (64-byte handle, exchanged by the host's own means) and summed by ONE kernel
+// that reads the peers over NVLink / NVSwitch (k_sum_peers: fixed rank order, so the result is bitwise reproducible).
+// No bootstrap: ncclCommInitRank plus NCCL's ring set-up cost 4-10 s at 8 ranks (profiles/README.md), more than the
+// whole 4K render takes on 8 GPUs; opening 7 handles costs milliseconds.
+// -------------------------------------------------------------------------------------------------------
+int vp_ipc_export(vp_context* c, const void* d_ptr, char* out64)
+{
+    if (!c || !d_ptr || !out64) return fail(VP_ERR_INVALID, "vp_ipc_export: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "VP_IPC_HANDLE_BYTES");
+    VP_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    VP_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(out64, &h, sizeof(h));
+    return VP_OK;
+}
+
+int vp_reduce_ipc(vp_context* c, void* d_sum, const char* peer_handles, int n_peers, int size, vp_stream stream)
+{
+    if (!c || !d_sum || (n_peers > 0 && !peer_handles) || n_peers < 0 || size < 0) return fail(VP_ERR_INVALID, "vp_reduce_ipc: bad arguments");
+    VP_CUDA(cudaSetDevice(c->device));
+    std::vector<const float4*> peers;
+    for (int i = 0; i < n_peers; i++)
+    {
+        const std::string key(peer_handles + (size_t)i * 64, 64);
+        void*             p = nullptr;
+        for (auto& kv : c->ipc_open)
+            if (kv.first == key) p = kv.second;
+        if (!p)
+        {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, key.data(), sizeof(h));
+            VP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_open.emplace_back(key, p);
+        }
+        peers.push_back(static_cast<const float4*>(p));
+    }
+    if (n_peers > 0) VP_CUDA(launch_sum_peers((float4*)d_sum, peers.data(), n_peers, size, (cudaStream_t)stream));
+    c->launches += (n_peers + 7) / 8;
+    return VP_OK;
+}
+
+int vp_ipc_close(vp_context* c)
+{
+    if (!c) return fail(VP_ERR_INVALID, "null context");
+    if (!c->ipc_open.empty())
+    {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (auto& kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
+        c->ipc_open.clear();
     }
     return VP_OK;
 }

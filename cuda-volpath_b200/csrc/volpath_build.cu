@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) k_fill_octets(const float* __restrict__ d
             float v[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) v[q] = tile[((cz + (q >> 2)) * 9 + cy + ((q >> 1) & 1)) * 9 + cx + (q & 1)];
-            size_t cell = (size_t)s * kBrickCells + c;
+            size_t cell = (size_t)s * kBrickCells + cell_local(cx, cy, cz);
             if (VT == kF32)
             {
                 float4* p = reinterpret_cast<float4*>(pool) + cell * 2;
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(256) k_opacity_octets(const __grid_constant__ 
             uint4   u;
             u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
             u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-            out[(size_t)s * kBrickCells + c] = u;
+            out[(size_t)s * kBrickCells + cell_local(cx, cy, cz)] = u;
         }
     }
 }
@@ -967,6 +967,34 @@ cudaError_t launch_accumulate(float4* dst, const float4* src, int size, cudaStre
 {
     if (size <= 0) return cudaSuccess;
     k_accumulate<<<(size + 255) / 256, 256, 0, stream>>>(dst, src, size);
+    return cudaGetLastError();
+}
+
+// dst += peers[0] + peers[1] + ... in that fixed order (bitwise reproducible): the reduce of a sample-sharded render over
+// PEER MEMORY -- the peer pointers are other GPUs' accumulators mapped through CUDA IPC, read over NVLink / NVSwitch
+struct PeerPtrs { const float4* p[8]; };
+__global__ void __launch_bounds__(256) k_sum_peers(float4* __restrict__ dst, const __grid_constant__ PeerPtrs peers, int n, int size)
+{
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < size; idx += gridDim.x * blockDim.x)
+    {
+        float4 a = dst[idx];
+        for (int q = 0; q < n; q++)
+        {
+            const float4 b = peers.p[q][idx];
+            a = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+        dst[idx] = a;
+    }
+}
+cudaError_t launch_sum_peers(float4* dst, const float4* const* peers, int n, int size, cudaStream_t stream)
+{
+    for (int i = 0; i < n; i += 8)
+    {
+        PeerPtrs pp{};
+        const int m = n - i < 8 ? n - i : 8;
+        for (int q = 0; q < m; q++) pp.p[q] = peers[i + q];
+        k_sum_peers<<<grid_for((size_t)size, 256, sms(16)), 256, 0, stream>>>(dst, pp, m, size);
+    }
     return cudaGetLastError();
 }
 

@@ -292,9 +292,24 @@ __device__ __forceinline__ uint32_t brick_slot(const Scene& S, int cx, int cy, i
     const uint32_t bit = 1u << (b & 31u);
     return (w.x & bit) ? w.y + __popc(w.x & (bit - 1u)) : kEmptyBrick;
 }
+// Order of the 512 cells inside a brick slot.  A miss fills a whole 128-byte line whatever the load asks for
+// (tools/sector_probe.cu), so VP_CELL_ORDER 1 makes a line a compact block instead of a run along x: the low three index
+// bits are (z0, y0, x0), i.e. 2x2x1 cells per line for 32-byte fp32 octets, 2x2x2 for 16-byte fp16 octets.
+#ifndef VP_CELL_ORDER
+#define VP_CELL_ORDER 0
+#endif
+__host__ __device__ __forceinline__ uint32_t cell_local(int cx, int cy, int cz)
+{
+    cx &= kBrick - 1; cy &= kBrick - 1; cz &= kBrick - 1;
+#if VP_CELL_ORDER
+    return (uint32_t)(((cz >> 1) << 7) | ((cy >> 1) << 5) | ((cx >> 1) << 3) | ((cz & 1) << 2) | ((cy & 1) << 1) | (cx & 1));
+#else
+    return (uint32_t)((cz << (2 * kBrickLog2)) | (cy << kBrickLog2) | cx);
+#endif
+}
 __device__ __forceinline__ size_t cell_in_slot(uint32_t slot, int cx, int cy, int cz)
 {
-    return (size_t)slot * kBrickCells + (((cz & (kBrick - 1)) << (2 * kBrickLog2)) | ((cy & (kBrick - 1)) << kBrickLog2) | (cx & (kBrick - 1)));
+    return (size_t)slot * kBrickCells + cell_local(cx, cy, cz);
 }
 
 // PARITY density fetch: restates the CUDA texture unit exactly as oracle/tex_emul.h does

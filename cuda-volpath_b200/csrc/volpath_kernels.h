@@ -23,6 +23,7 @@ cudaError_t launch_render_wave(const Scene& S, float4* d_sum, int first_frame, i
                                const vp_param& P, unsigned long long* d_work, unsigned long long* d_stats, int num_sms,
                                cudaStream_t stream);
 cudaError_t launch_accumulate(float4* dst, const float4* src, int size, cudaStream_t stream);
+cudaError_t launch_sum_peers(float4* dst, const float4* const* peers, int n, int size, cudaStream_t stream);
 cudaError_t launch_resolve(float4* dst, const float4* src, int size, float scale, float gamma, cudaStream_t stream);
 
 // --- scene build (volpath_build.cu) ---------------------------------------------------------------------

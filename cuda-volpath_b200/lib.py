@@ -75,6 +75,9 @@ SIGNATURES = {
     "vp_reduce_nccl": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "vp_nccl_destroy": (c_int, [c_vp]),
     "vp_reduce": (c_int, [ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_int, c_int, c_int]),
+    "vp_ipc_export": (c_int, [c_vp, c_vp, ctypes.c_char_p]),
+    "vp_reduce_ipc": (c_int, [c_vp, c_vp, ctypes.c_char_p, c_int, c_int, c_vp]),
+    "vp_ipc_close": (c_int, [c_vp]),
     "vp_get_bounds_voxel": (c_int, [c_vp, c_fp]),
     "vp_get_bounds_cell": (c_int, [c_vp, c_fp, ctypes.POINTER(c_int)]),
     "vp_get_half_tables": (c_int, [c_vp, c_vp, c_vp, c_fp, ctypes.POINTER(c_int)]),

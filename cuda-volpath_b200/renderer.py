@@ -137,6 +137,28 @@ class Renderer:
     def nccl_destroy(self):
         _l.check(self.L.vp_nccl_destroy(self.h))
 
+    # ---- the same reduce over peer memory (CUDA IPC, one node): no communicator, no bootstrap ---------------------
+    def dev_alloc(self, nbytes):
+        """A plain cudaMalloc block on this context's device, zero-filled (IPC handles need base pointers)."""
+        import torch  # only to make this context's device current for the allocation
+
+        with torch.cuda.device(self.device):
+            p = self.L.vp_dev_alloc(nbytes)
+        if not p:
+            raise _l.VolpathError("out of device memory")
+        return p
+
+    def ipc_export(self, d_base_ptr):
+        buf = ctypes.create_string_buffer(64)
+        _l.check(self.L.vp_ipc_export(self.h, d_base_ptr, buf))
+        return buf.raw
+
+    def reduce_ipc(self, d_sum_ptr, peer_handles, size, stream=None):
+        """d_sum += every peer accumulator (list of 64-byte handles, rank order), read over NVLink through CUDA IPC."""
+        blob = b"".join(peer_handles)
+        assert len(blob) == 64 * len(peer_handles)
+        _l.check(self.L.vp_reduce_ipc(self.h, d_sum_ptr, blob, len(peer_handles), size, stream))
+
     # ---- introspection -----------------------------------------------------------------------------------
     def bounds_voxel(self):
         nx, ny, nz = self.dims

@@ -169,6 +169,16 @@ int vp_nccl_init(vp_context* ctx, int n_ranks, int rank, const char* id128);
 int vp_reduce_nccl(vp_context* ctx, const void* d_send_float4, void* d_recv_float4, int size, int root, vp_stream stream);
 int vp_nccl_destroy(vp_context* ctx);
 int vp_reduce(vp_context** ctxs, void** d_sums_float4, int n, int size, int root);
+/* The same reduce over PEER MEMORY, single node, no communicator and no bootstrap (NCCL's costs 4-10 s at 8 ranks): every
+ * rank exports its accumulator -- a cudaMalloc / vp_dev_alloc BASE pointer -- with vp_ipc_export (64 bytes, carried to the
+ * root by the host's own means); the root maps the peers through CUDA IPC (cached per context) and ONE kernel adds them
+ * into its own sum in rank order, reading the peers over NVLink / NVSwitch.  The caller orders the processes: the peers'
+ * renders are complete (their streams synchronised, then a host-level barrier) before the root calls vp_reduce_ipc, and
+ * the peers leave their buffers alone until the root's stream has finished (a second barrier). */
+#define VP_IPC_HANDLE_BYTES 64
+int vp_ipc_export(vp_context* ctx, const void* d_base_ptr, char* out64);
+int vp_reduce_ipc(vp_context* ctx, void* d_sum_float4, const char* peer_handles64, int n_peers, int size, vp_stream stream);
+int vp_ipc_close(vp_context* ctx);
 /* vp_precompute_opacity for a multi-process host whose ranks hold the same volume (after vp_nccl_init): rank r sweeps 1/G
  * of the production table and an in-place ncclAllGather completes it on every rank -- the one setup step that is worth
  * sharding (0.55 s on one B200 at the full C2 grid).  Collective: every rank must call it.  Without a communicator it is

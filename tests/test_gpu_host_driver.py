@@ -138,3 +138,60 @@ def test_nccl_reduce_through_the_c_abi_single_rank():
         r.reduce_nccl(a.data_ptr(), b.data_ptr(), 1000, root=3, stream=s)
     r.nccl_destroy()
     r.close()
+
+
+def _ipc_child(conn, root):
+    import sys
+
+    sys.path.insert(0, root)
+    import numpy as np
+
+    import cuda_volpath_b200 as vp
+
+    r = vp.Renderer(0)
+    n = 5000
+    p = r.dev_alloc(n * 16)
+    a = (np.arange(n * 4, dtype=np.float32) * 0.25).reshape(n, 4)
+    assert r.L.vp_host_to_dev(p, a.ctypes.data, a.nbytes) == 0
+    r.sync()
+    conn.send(r.ipc_export(p))
+    conn.recv()  # the parent has read the buffer
+    r.L.vp_dev_free(p)
+    r.close()
+
+
+def test_peer_memory_reduce_through_cuda_ipc_two_processes():
+    """vp_ipc_export / vp_reduce_ipc: another PROCESS's accumulator is mapped through its 64-byte IPC handle and added by
+    one kernel in rank order (here both processes share GPU 0; across GPUs the same kernel reads over NVLink:
+    tests/test_gpu_multi_rank.py, bench.py --gpus N)."""
+    import multiprocessing as mp
+
+    import cuda_volpath_b200 as vp
+
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    proc = ctx.Process(target=_ipc_child, args=(child, ROOT))
+    proc.start()
+    try:
+        assert parent.poll(120), "child did not export a handle"
+        handle = parent.recv()
+        assert len(handle) == 64
+        r = vp.Renderer(0)
+        n = 5000
+        mine = np.full((n, 4), 2.0, np.float32)
+        p = r.dev_alloc(n * 16)
+        assert r.L.vp_host_to_dev(p, mine.ctypes.data, mine.nbytes) == 0
+        r.reduce_ipc(p, [handle], n)
+        r.reduce_ipc(p, [handle], n)  # the mapping is cached: a second reduce adds the peer again
+        r.sync()
+        out = np.empty_like(mine)
+        assert r.L.vp_dev_to_host(out.ctypes.data, p, out.nbytes) == 0
+        want = mine + 2 * (np.arange(n * 4, dtype=np.float32) * 0.25).reshape(n, 4)
+        assert np.array_equal(out, want)
+        r.L.vp_ipc_close(r.h)
+        r.L.vp_dev_free(p)
+        r.close()
+    finally:
+        parent.send("done")
+        proc.join(60)
+    assert proc.exitcode == 0

@@ -33,10 +33,23 @@ acc = torch.zeros(96, 128, 4, device="cuda")
 first, count, stride = vp.frames_for_rank(11, 37, rank, world)
 s = torch.cuda.current_stream().cuda_stream
 r.render_kernel(acc.data_ptr(), first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=s)
+# the same sums once more through peer memory (CUDA IPC): plain cudaMalloc blocks, handles through the TCP store
+blk = r.dev_alloc(128 * 96 * 16)
+r.render_kernel(blk, first, P, mode=vp.MODE_FAST, n_frames=count, frame_stride=stride, stream=s)
+torch.cuda.synchronize()
+store = dist.distributed_c10d._get_default_store()
+store.set("h%d" % rank, r.ipc_export(blk))
 r.reduce_nccl(acc.data_ptr(), acc.data_ptr() if rank == 0 else None, 128 * 96, root=0, stream=s)
 torch.cuda.synchronize()
+dist.barrier()
 if rank == 0:
+    r.reduce_ipc(blk, [bytes(store.get("h%d" % q)) for q in range(1, world)], 128 * 96, stream=s)
+    torch.cuda.synchronize()
+    ipc = np.empty((96, 128, 4), np.float32)
+    assert r.L.vp_dev_to_host(ipc.ctypes.data, blk, ipc.nbytes) == 0
+    np.save(os.environ["VP_OUT"] + "_ipc.npy", ipc)
     np.save(os.environ["VP_OUT"] + "_img.npy", acc.cpu().numpy()); np.save(os.environ["VP_OUT"] + "_tab.npy", tab)
+dist.barrier()
 dist.barrier(); r.close(); dist.destroy_process_group()
 '''
 
@@ -72,3 +85,5 @@ def test_two_ranks_sharded_opacity_and_nccl_reduce_equal_one_gpu(tmp_path):
     assert img1[..., 3].max() / 37 > 20                     # deep paths: the opacity-table branch is exercised
     assert np.array_equal(img1[..., 3], img2[..., 3])       # every (pixel, frame) exactly once, same paths
     assert np.allclose(img1[..., :3], img2[..., :3], rtol=1e-5, atol=1e-6)
+    ipc = np.load(out + "_ipc.npy")                         # vp_reduce_ipc: the same sums over peer memory
+    assert np.array_equal(ipc[..., 3], img2[..., 3]) and np.allclose(ipc[..., :3], img2[..., :3], rtol=1e-5, atol=1e-6)

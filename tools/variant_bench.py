@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--julia", action="store_true")
     ap.add_argument("--sync-frames", type=int, default=0, help="also time N one-frame launches with a sync after each (the reference host's pattern)")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--store", default="f32", choices=["f32", "f16"])
     a = ap.parse_args()
     W, H = a.image
     r = vp.Renderer(0)
@@ -37,7 +38,7 @@ def main():
     if a.julia:
         r.set_julia()
     else:
-        r.generate_cloud(*a.dims, seed=0, bounds=vp.BOUNDS_CELL)
+        r.generate_cloud(*a.dims, seed=0, bounds=vp.BOUNDS_CELL, store=vp.VOXEL_F16 if a.store == "f16" else vp.VOXEL_F32)
     r.set_texture_filter_mode(True)
     r.init_envmap(env)
     r.set_sun(sd, sp)

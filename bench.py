@@ -430,6 +430,8 @@ def main():
         store = dist.distributed_c10d._get_default_store()
         store.set("volpath_ipc_%d" % rank, r.ipc_export(total_ptr))
         peer_handles = [bytes(store.get("volpath_ipc_%d" % q)) for q in range(1, world)] if rank == 0 else []
+        if rank == 0:
+            r.reduce_ipc(total_ptr, peer_handles, 0, stream=stream)  # maps the peers now (cudaIpcOpenMemHandle + peer access), adds nothing
     if reduce_step:
         nccl_thread.join()
         bufs = [torch.zeros(H, W, 4, device="cuda", dtype=torch.float32) for _ in range(2)]

@@ -59,6 +59,10 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #ifndef VP_INLINE_SEG
 #define VP_INLINE_SEG 0
 #endif
+#ifndef VP_STEP_FLAT
+#define VP_STEP_FLAT 1  // gray media: branch-free step decision (same arithmetic, same samples): 1088 -> 1100 M/s at full C2; with the
+                        // brick-skip variants it loses 0.9 % (C4), so those keep the branches
+#endif
 #ifndef VP_SUN_NO_SLAB
 #define VP_SUN_NO_SLAB 0  // experiment: sun shadow walks ended by the sun-clear distance alone (+0.7 % at full C2) -- NOT exact when medium
                           // touches the box wall: clamp addressing extends the border voxels half a voxel beyond the box
@@ -397,6 +401,31 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                         if (den == 0.0f) { if (st & kShadow) c_zero_s++; else c_zero_t++; }
                     }
                 }
+#if VP_STEP_FLAT
+                if (GRAY && !MIS && (LYX == 1 || LYX == 2))  // the two production layouts without brick skipping: +1.0 % at full C2
+                {
+                    // branch-free decision for gray media: the three outcomes (shadow step / segment end / tracking event)
+                    // are evaluated by every stepping lane and selected, instead of three divergent branches in a row
+                    const bool  shadow = (st & kShadow) != 0, ctrl = (st & kLimIsCtrl) != 0;
+                    const float t_den = sig_t.x * den - sigc, s_den = sig_s.x * den - sigc, n_den = maj - t_den;
+                    const float at = fabsf(t_den), an = fabsf(n_den), c = at + an;
+                    const bool  hit = u1 * c < at;
+                    const float w   = (hit ? s_den : n_den) * __fdividef(c, maj * (hit ? at : an));
+                    const bool  track = !shadow && !past;
+                    const bool  kill  = shadow && !past && (u1 < sig_t.x * (den * inv));
+                    const bool  to_scat = (track && hit) || (!shadow && past && ctrl);
+                    const bool  to_seg  = !shadow && past && !ctrl;
+                    const bool  sh_done = shadow && (past || kill);
+                    T.x  = track ? T.x * w : T.x;
+                    o    = f3(to_scat ? pos.x : o.x, to_scat ? pos.y : o.y, to_scat ? pos.z : o.z);
+                    dist = to_seg ? lim : dist;
+                    uint32_t ns = to_scat ? (uint32_t)kModeScat : st;
+                    ns = to_seg ? (uint32_t)kModeSeg : ns;
+                    ns = sh_done ? (kModeSeg | kNeedRay | kShadowDone | (kill ? (kKillX | kKillY | kKillZ) : 0u)) : ns;
+                    st = ns;
+                }
+                else
+#endif
                 if (st & kShadow)
                 {
                     if (!past)

@@ -174,7 +174,8 @@ int vp_reduce(vp_context** ctxs, void** d_sums_float4, int n, int size, int root
  * root by the host's own means); the root maps the peers through CUDA IPC (cached per context) and ONE kernel adds them
  * into its own sum in rank order, reading the peers over NVLink / NVSwitch.  The caller orders the processes: the peers'
  * renders are complete (their streams synchronised, then a host-level barrier) before the root calls vp_reduce_ipc, and
- * the peers leave their buffers alone until the root's stream has finished (a second barrier). */
+ * the peers leave their buffers alone until the root's stream has finished (a second barrier).  Mappings are cached per
+ * context (keyed by the handle bytes; size 0 just maps) until vp_ipc_close or vp_destroy. */
 #define VP_IPC_HANDLE_BYTES 64
 int vp_ipc_export(vp_context* ctx, const void* d_base_ptr, char* out64);
 int vp_reduce_ipc(vp_context* ctx, void* d_sum_float4, const char* peer_handles64, int n_peers, int size, vp_stream stream);

@@ -63,6 +63,9 @@ constexpr int      kFastThreads  = VP_FAST_THREADS;  // CTA size; the CTA counts
 #define VP_STEP_FLAT 1  // gray media: branch-free step decision (same arithmetic, same samples): 1088 -> 1100 M/s at full C2; with the
                         // brick-skip variants it loses 0.9 % (C4), so those keep the branches
 #endif
+#ifndef VP_STEP_FLAT_CHROMA
+#define VP_STEP_FLAT_CHROMA 0
+#endif
 #ifndef VP_SUN_NO_SLAB
 #define VP_SUN_NO_SLAB 0  // experiment: sun shadow walks ended by the sun-clear distance alone (+0.7 % at full C2) -- NOT exact when medium
                           // touches the box wall: clamp addressing extends the border voxels half a voxel beyond the box
@@ -422,6 +425,36 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm(GRAY, MIS)) k_r
                     uint32_t ns = to_scat ? (uint32_t)kModeScat : st;
                     ns = to_seg ? (uint32_t)kModeSeg : ns;
                     ns = sh_done ? (kModeSeg | kNeedRay | kShadowDone | (kill ? (kKillX | kKillY | kKillZ) : 0u)) : ns;
+                    st = ns;
+                }
+                else
+#endif
+#if VP_STEP_FLAT_CHROMA
+                if (!GRAY && !MIS && (LYX == 1 || LYX == 2))
+                {
+                    // the same for chromatic media: per-channel kill flags accumulate over the steps of a shadow walk
+                    const bool   shadow = (st & kShadow) != 0, ctrl = (st & kLimIsCtrl) != 0;
+                    const float3 t_den = sig_t * den - f3(sigc), s_den = sig_s * den - f3(sigc), n_den = f3(maj) - t_den;
+                    const float  Ps = fabsf(t_den.x * T.x) + fabsf(t_den.y * T.y) + fabsf(t_den.z * T.z);
+                    const float  Pn = fabsf(n_den.x * T.x) + fabsf(n_den.y * T.y) + fabsf(n_den.z * T.z);
+                    const float  c  = Ps + Pn;
+                    const bool   hit = u1 * c < Ps;
+                    const float  k   = __fdividef(c, maj * (hit ? Ps : Pn));
+                    const bool   track = !shadow && !past;
+                    const float  q = den * inv;
+                    uint32_t     kills = st & (kKillX | kKillY | kKillZ);
+                    if (shadow && !past)
+                        kills |= (u1 < sig_t.x * q ? kKillX : 0u) | (u1 < sig_t.y * q ? kKillY : 0u) | (u1 < sig_t.z * q ? kKillZ : 0u);
+                    const bool to_scat = (track && hit) || (!shadow && past && ctrl);
+                    const bool to_seg  = !shadow && past && !ctrl;
+                    const bool sh_done = shadow && (past || kills == (kKillX | kKillY | kKillZ));
+                    if (track) T = T * ((hit ? s_den : n_den) * k);
+                    o    = f3(to_scat ? pos.x : o.x, to_scat ? pos.y : o.y, to_scat ? pos.z : o.z);
+                    dist = to_seg ? lim : dist;
+                    uint32_t ns = shadow ? (st | kills) : st;
+                    ns = to_scat ? (uint32_t)kModeScat : ns;
+                    ns = to_seg ? (uint32_t)kModeSeg : ns;
+                    ns = sh_done ? (kModeSeg | kNeedRay | kShadowDone | kills) : ns;
                     st = ns;
                 }
                 else

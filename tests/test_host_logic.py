@@ -111,3 +111,25 @@ def test_sample_sharded_render_reduces_to_the_single_rank_image(vp, oracle, gold
     want = oracle.render(P, 0, 5)
     assert np.array_equal(got[..., 3], want[..., 3])  # scatter counts: integers, exact under any order
     assert np.allclose(got[..., :3], want[..., :3], rtol=1e-6, atol=1e-7)
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """The JSON line bench.py printed on a B200 at the end of the round (profiles/r2_bench_c2.json): the keys the
+    measurement contract names, with internally consistent numbers."""
+    import json
+
+    j = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_c2.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "check", "rmse"):
+        assert k in j, k
+    assert j["metric"] == "path-samples/s" and j["n_gpus"] == 1 and j["gpu_launches"] == j["steps"] and "workload" in j["config"]
+    roof = j["roofline"]
+    assert roof["bound"] == "hbm" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["traffic"] > 0
+    paths = 1920 * 1080 * j["config"]["frames_per_step"] * j["steps"]
+    assert abs(j["value"] - paths / (j["ms_per_step"] * j["steps"] * 1e-3)) / j["value"] < 1e-6
+    assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0 and j["e2e"]["value"] < j["value"] * 1.02
+    cb = j["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and "sample" in cb and "gpu_same_sample" in cb
+    chk = j["check"]
+    assert chk["ok"] and chk["scatter_rel"] <= 0.01 and chk["mean_rel"] <= 0.005
+    assert j["rmse"]["time_to_rmse_ratio"] > 1 and len(j["rmse"]["rmse_ours"]) == len(j["rmse"]["checkpoints_spp"])

@@ -294,6 +294,12 @@ def check_block(vp, device, dims, over, subset=(480, 270), frames=256):
             "bounds_voxel_bytes": st["bounds_voxel_bytes"], "setup_s": round(setup, 2)}
 
 
+def _timed_nccl_boot(vp, r, rank, world):
+    t0 = time.perf_counter()
+    vp.init_nccl_via_store(r, rank, world)
+    return time.perf_counter() - t0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -422,16 +428,40 @@ def main():
     total = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)  # N = 1 / --reduce end: this rank's accumulator; the image on the root
     total_ptr = total.data_ptr()
     reduce_step = world > 1 and args.reduce == "step"
+    ipc_fallback = None
     if use_ipc:
         # peer-memory reduce: the accumulator is a plain cudaMalloc block (IPC handles need base pointers); its 64-byte
-        # handle travels to the root through torch.distributed's TCP store
-        del total
-        total_ptr = r.dev_alloc(W * H * 16)
+        # handle travels to the root through torch.distributed's TCP store.  Where CUDA IPC is not permitted (some container
+        # set-ups) every rank learns it here and the job falls back to the NCCL transport -- loudly, in the JSON line.
+        ok, ipc_ptr, peer_handles = 1, None, []
         store = dist.distributed_c10d._get_default_store()
-        store.set("volpath_ipc_%d" % rank, r.ipc_export(total_ptr))
-        peer_handles = [bytes(store.get("volpath_ipc_%d" % q)) for q in range(1, world)] if rank == 0 else []
+        try:
+            if os.environ.get("VOLPATH_BENCH_NO_IPC"):
+                raise RuntimeError("disabled by VOLPATH_BENCH_NO_IPC")
+            ipc_ptr = r.dev_alloc(W * H * 16)
+            store.set("volpath_ipc_%d" % rank, r.ipc_export(ipc_ptr))
+        except Exception as e:
+            ok, ipc_fallback = 0, repr(e)[:200]
+            store.set("volpath_ipc_%d" % rank, b"")
         if rank == 0:
-            r.reduce_ipc(total_ptr, peer_handles, 0, stream=stream)  # maps the peers now (cudaIpcOpenMemHandle + peer access), adds nothing
+            try:
+                peer_handles = [bytes(store.get("volpath_ipc_%d" % q)) for q in range(1, world)]
+                if ok and all(len(h) == 64 for h in peer_handles):
+                    r.reduce_ipc(ipc_ptr, peer_handles, 0, stream=stream)  # maps the peers now (cudaIpcOpenMemHandle + peer access), adds nothing
+                else:
+                    ok = 0
+            except Exception as e:
+                ok, ipc_fallback = 0, repr(e)[:200]
+        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            del total
+            total_ptr = ipc_ptr
+        else:
+            use_ipc = False
+            ipc_fallback = ipc_fallback or "CUDA IPC unavailable on another rank"
+            nccl_thread = threading.Thread(target=lambda: nccl_info.update(s=_timed_nccl_boot(vp, r, rank, world)), daemon=True)
+            nccl_thread.start()
     if reduce_step:
         nccl_thread.join()
         bufs = [torch.zeros(H, W, 4, device="cuda", dtype=torch.float32) for _ in range(2)]
@@ -607,6 +637,8 @@ def main():
            "sample-index sharding x%d (%s scaling: %d frames per step %s), %s"
            % (world, "strong" if strong else "weak", step_frames, "in total" if strong else "= %d per GPU" % fps, how))
     par += "; consecutive steps alternate over %d render stream(s)" % len(rs)
+    if ipc_fallback:
+        par += "; CUDA IPC was NOT available (%s): fell back to the NCCL transport" % ipc_fallback
     line = {"metric": "path-samples/s", "value": value, "unit": "path-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if (strong or world == 1) else "weak",

@@ -810,9 +810,14 @@ static int precompute_opacity_impl(vp_context* c, const float* dir3, bool sharde
     c->S.opacity_oct  = nullptr;
     const float3 dir  = make_float3(dir3[0], dir3[1], dir3[2]);
     const size_t slots = c->n_slots ? c->n_slots : 1;
-    cudaEvent_t  t0 = nullptr, t1 = nullptr;
-    VP_CUDA(cudaEventCreate(&t0));
-    VP_CUDA(cudaEventCreate(&t1));
+    struct Ev
+    {
+        cudaEvent_t e = nullptr;
+        ~Ev() { if (e) cudaEventDestroy(e); }
+    } ev0, ev1;
+    VP_CUDA(cudaEventCreate(&ev0.e));
+    VP_CUDA(cudaEventCreate(&ev1.e));
+    cudaEvent_t t0 = ev0.e, t1 = ev1.e;
     cudaEventRecord(t0, 0);
     int rc = VP_OK;
     // (1) the bit-faithful per-voxel march (K.cu:483-524) for VP_MODE_PARITY: only contexts that can run that mode
@@ -846,8 +851,6 @@ static int precompute_opacity_impl(vp_context* c, const float* dir3, bool sharde
     cudaError_t e = cudaDeviceSynchronize();
     if (rc == VP_OK && e != cudaSuccess) rc = fail((int)e, "vp_precompute_opacity: %s", cudaGetErrorString(e));
     if (rc == VP_OK) cudaEventElapsedTime(&c->opacity_ms, t0, t1);
-    cudaEventDestroy(t0);
-    cudaEventDestroy(t1);
     if (rc != VP_OK)
     {
         cudaGetLastError();
@@ -1282,8 +1285,11 @@ int vp_reduce(vp_context** ctxs, void** d_sums, int n, int size, int root)
         VP_CUDA(cudaSetDevice(ctxs[i]->device));
         VP_CUDA(cudaDeviceSynchronize());
     }
-    static std::vector<int>   cached_devs;
-    static std::vector<void*> cached_comms;
+    // one communicator set per device list, shared by all callers of this process
+    static std::mutex           cache_lock;
+    std::lock_guard<std::mutex> guard(cache_lock);
+    static std::vector<int>     cached_devs;
+    static std::vector<void*>   cached_comms;
     std::vector<int>          devs(n);
     for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
     const bool use_nccl = nccl().ok && !env_flag("VOLPATH_REDUCE_P2P");

@@ -199,11 +199,17 @@ __device__ __forceinline__ float ldg_keep(const float* a)
     asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(l2_policy_keep()));
     return v;
 }
+#ifndef VP_TABLE_L1_KEEP
+#define VP_TABLE_L1_KEEP 0  // experiment: 1 = the small tables are also loaded with L1::evict_last
+#endif
 __device__ __forceinline__ uint32_t ldg_keep(const uint32_t* a)
 {
     if (!VP_L2_KEEP) return __ldg(a);
     uint32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(l2_policy_keep()));
+    if (VP_TABLE_L1_KEEP)
+        asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(l2_policy_keep()));
+    else
+        asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(l2_policy_keep()));
     return v;
 }
 __device__ __forceinline__ uint16_t ldg_keep(const uint16_t* a)
@@ -217,7 +223,10 @@ __device__ __forceinline__ uint2 ldg_keep(const uint2* a)
 {
     if (!VP_L2_KEEP) return __ldg(a);
     uint2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_policy_keep()));
+    if (VP_TABLE_L1_KEEP)
+        asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_policy_keep()));
+    else
+        asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_policy_keep()));
     return v;
 }
 __device__ __forceinline__ void ldg256_stream(const void* a, float v[8])
@@ -249,6 +258,17 @@ __device__ __forceinline__ void load_octet(const void* pool, size_t cell_index, 
         asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                      : "l"(p));
+    }
+#ifndef VP_OCTET_L1
+#define VP_OCTET_L1 0  // experiment: 1 = octet loads do not allocate in L1 (leave it to the directory and the bound tables)
+#endif
+    else if (VT == kF32 && VP_OCTET_L1 == 1)
+    {
+        const float4* p = reinterpret_cast<const float4*>(pool) + cell_index * 2;
+        float4        a, b;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 1));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
     else if (VT == kF32)
     {

@@ -88,7 +88,10 @@ __host__ __device__ constexpr int fast_ctas_per_sm(bool gray, bool mis)
     return (mis ? 8 : (gray ? kFastCtasPerSm : (kFastCtasPerSm > VP_CHROMA_CTAS ? VP_CHROMA_CTAS : kFastCtasPerSm))) * (128 / kFastThreads);
 }
 constexpr uint32_t kFull         = 0xffffffffu;
-constexpr uint32_t kClaim        = 256;  // items per warp-level claim (large launches); small launches claim less, see launch_fast_t
+#ifndef VP_CLAIM
+#define VP_CLAIM 64  // 512 / 256 / 128 / 96 / 64 / 32 items per claim: 1058 / 1093 / 1116 / 1120 / 1120 / 1115 M/s (full C2, 64-frame launches)
+#endif
+constexpr uint32_t kClaim        = VP_CLAIM;  // items per warp-level claim (large launches); small launches claim less, see launch_fast_t
 // vote weights of the four blocks {-, path, scatter, segment, step}: a block runs when lanes x weight is largest, so a
 // lower weight makes an expensive block wait for more lanes (tuned on B200, profiles/)
 #ifndef VP_W_PATH

@@ -1400,7 +1400,7 @@ int vp_ipc_close(vp_context* c)
 static vp_context* g_shim      = nullptr;
 // Default renderer of the render_kernel shim: the production megakernel (the same estimator in distribution; 3.5x the
 // reference kernel when frames are batched or not synchronised one by one, profiles/README.md).  VP_MODE_PARITY -- fixed-seed
-// traces equal to the reference kernel's, at 0.82x its speed (software texture emulation) -- by vp_shim_set_mode(0) or
+// traces equal to the reference kernel's, at 0.83x its speed (software texture emulation) -- by vp_shim_set_mode(0) or
 // VOLPATH_SHIM_MODE=parity.
 static int shim_default_mode()
 {

@@ -234,7 +234,7 @@ void gamma_correct(vp_float4* dst, vp_float4* src, int size, float scale, float 
 void render_kernel(vp_dim3 gridSize, vp_dim3 blockSize, vp_float4* d_output, int spp, const vp_param* p);
 /* which renderer the render_kernel shim uses.  Default VP_MODE_FAST (the same estimator in distribution, verified against
  * the reference kernel; environment VOLPATH_SHIM_MODE=parity|fast|wave overrides the default).  VP_MODE_PARITY reproduces
- * the reference kernel's fixed-seed traces (1e-5 relative) at 0.82x its speed (profiles/r2_parity_mode_vs_ref.json).
+ * the reference kernel's fixed-seed traces (1e-5 relative) at 0.83x its speed (profiles/r2_parity_mode_vs_ref.json).
  * VP_MODE_FAST: consecutive one-frame launches rotate over four internal BLOCKING streams, so the
  * long tail of frame n overlaps frame n + 1 while the host does not synchronise.  Blocking streams order themselves against
  * the legacy default stream exactly like the reference's own launches, so a host that uses the default stream,
